@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""bench.py — Msamples/s (pixel*spp/s) of the path-tracing hot path on helmet.glb 1920x1080.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path
+    python bench.py --impl reference --steps K --warmup W    # the CPU restatement on the host cores
+
+A step = one full frame of BASELINE.json's headline config (helmet.glb, 1920x1080, 1024 spp,
+8 bounces, synthetic environment) rendered by N GPUs: every rank renders spp/N samples of every
+pixel into an f32 accumulator (spp-range split), the accumulators are summed to rank 0
+with one NCCL reduce, rank 0 resolves to u8 sRGB.  The total work is fixed => "scaling": "strong".
+
+Keys beyond the base contract: `roofline` (the trace kernel against the measured FP32 issue
+ceiling, the bound SURVEY §8d derives — not HBM, not tensor), `cpu_baseline` (the oracle timed on
+the host cores on a bounded sample), `e2e` (the same frame through the reference entry point
+render_thread_proc with HOST buffers: scene upload H2D and image D2H inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+MODEL = os.path.join(ROOT, "assets", "models", "helmet.glb")
+METRIC = "Msamples/s (pixel*spp/s), helmet.glb 1920x1080"
+UNIT = "Msamples/s"
+COUNTER_NAMES = ["rays", "nodes", "leaves", "accepts", "shades", "misses", "passthrough", "samples"]
+
+# FLOP model of SURVEY §8(d): per box test 25 lane-ops x 8, per triangle 57 x 8, +33 per accepted
+# hit, ~700 per textured shade, ~90 per environment lookup, 40 per primary ray.
+FLOP_NODE, FLOP_LEAF, FLOP_ACCEPT, FLOP_SHADE, FLOP_ENV, FLOP_RAYGEN = 200.0, 456.0, 33.0, 700.0, 90.0, 40.0
+# cache-level bytes per unit of work (same section): 192 B per node, 288 B per leaf, 112 B per
+# accepted record, 4 taps x 4 textures x 4 B + 80 B material per shade
+BYTES_NODE, BYTES_LEAF, BYTES_ACCEPT, BYTES_SHADE = 192.0, 288.0, 112.0, 144.0
+
+
+def algorithmic_flops(c: dict) -> float:
+    return (FLOP_RAYGEN * c["samples"] + FLOP_NODE * c["nodes"] + FLOP_LEAF * c["leaves"] +
+            FLOP_ACCEPT * c["accepts"] + FLOP_SHADE * c["shades"] + FLOP_ENV * c["misses"])
+
+
+def workload_config(args, parallelism: str) -> dict:
+    return {"workload": f"helmet.glb {args.width}x{args.height} {args.spp}spp max_bounces {args.bounces}",
+            "model": "helmet.glb (15452 triangles, depth-4 8-ary BVH, 4x 2048^2 textures)",
+            "environment": "procedural equirect 2048x1024 (reference background.png is not in its tree)",
+            "seed_mode": "per-(pixel,sample) rt_path_seed, user_seed 0", "parallelism": parallelism}
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons during the timed region (NVML, else nvidia-smi)."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_flag = threading.Event()
+
+    def run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            names = {getattr(pynvml, k): k for k in dir(pynvml) if k.startswith("nvmlClocksThrottleReason")
+                     or k.startswith("nvmlClocksEventReason")}
+            while not self._stop_flag.is_set():
+                self.samples.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                try:
+                    mask = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    for bit, name in names.items():
+                        if isinstance(bit, int) and bit and mask & bit and "None" not in name and "All" not in name:
+                            self.reasons.add(name.replace("nvmlClocksThrottleReason", "").replace("nvmlClocksEventReason", ""))
+                except Exception:
+                    pass
+                time.sleep(0.2)
+        except Exception:
+            import subprocess
+            q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+                "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+            while not self._stop_flag.is_set():
+                try:
+                    out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                         capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                    self.samples.append(int(out[0]))
+                    self.max_mhz = int(out[1])
+                    for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], out[2:]):
+                        if "Active" in v and "Not" not in v:
+                            self.reasons.add(name)
+                except Exception:
+                    pass
+                time.sleep(0.2)
+
+    def finish(self) -> dict:
+        self._stop_flag.set()
+        self.join(timeout=3)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "n_samples": len(s)}
+
+
+def host_threads() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_reference_rate(args, loaded=None, target_seconds: float = 15.0):
+    """Times the CPU restatement (oracle; oracle/_ref when it exists) on all host threads on a bounded
+    sample of the SAME frame: full resolution, reduced spp (the rate does not depend on spp)."""
+    import oracle_ffi
+    from raytracing_c_b200 import driver
+    own = loaded is None
+    if own:
+        loaded = driver.load_scene(MODEL, shader_proc=oracle_ffi.shader_proc(), background_proc=oracle_ffi.background_proc())
+    cores = host_threads()
+    try:
+        t0 = time.perf_counter()
+        oracle_ffi.render(loaded, args.width, args.height, 1, args.bounces, n_threads=cores, want_accum=False)
+        t1 = time.perf_counter() - t0
+        spp = max(1, min(64, int(target_seconds / max(t1, 1e-3))))
+        t0 = time.perf_counter()
+        oracle_ffi.render(loaded, args.width, args.height, spp, args.bounces, n_threads=cores, want_accum=False)
+        dt = time.perf_counter() - t0
+    finally:
+        if own:
+            loaded.close()
+    rate = args.width * args.height * spp / dt / 1e6
+    return {"value": round(rate, 4), "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"helmet.glb {args.width}x{args.height} at {spp} spp ({dt:.1f} s of CPU work, AVX2 oracle, "
+                      f"reference chunk scheduler, {cores} threads)"}, spp, dt
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle_ffi
+    from raytracing_c_b200 import driver
+    loaded = driver.load_scene(MODEL, shader_proc=oracle_ffi.shader_proc(), background_proc=oracle_ffi.background_proc())
+    cores = host_threads()
+    spp = args.cpu_spp
+    per_step = []
+    try:
+        for i in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            oracle_ffi.render(loaded, args.width, args.height, spp, args.bounces, n_threads=cores, want_accum=False)
+            if i >= args.warmup:
+                per_step.append(time.perf_counter() - t0)
+    finally:
+        loaded.close()
+    total = sum(per_step)
+    value = args.width * args.height * spp * len(per_step) / total / 1e6
+    line = {"impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * total / len(per_step), 3),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, "cpu"),
+            "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"each step = the same frame at {spp} spp instead of {args.spp} "
+                                       f"(rate is spp-independent); AVX2 oracle, {cores} threads"},
+            "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def run_gpu(args) -> None:
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from raytracing_c_b200 import driver, gpu_lib
+    from raytracing_c_b200._ffi import gpu_check
+
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    gpu = gpu_lib()
+    gpu_check(gpu.rt_gpu_init(local))
+    dev = torch.device("cuda", local)
+
+    W, H, SPP, B = args.width, args.height, args.spp, args.bounces
+    if SPP % (8 * world):
+        raise SystemExit("spp must be a multiple of 8 x n_gpus (jitter batches are 8 samples, raytracer.c:641-697)")
+    s_begin, s_end = rank * SPP // world, (rank + 1) * SPP // world
+    slice_spp = args.slice
+
+    t0 = time.perf_counter()
+    loaded = driver.load_scene(MODEL)          # Shader/Background procs = the GPU library's own identities
+    t_load = time.perf_counter() - t0
+    driver.register_callbacks(loaded)
+    scene_ref = C.byref(loaded.scene)
+    t0 = time.perf_counter()
+    gpu_check(gpu.rt_gpu_scene_upload(scene_ref))
+    torch.cuda.synchronize()
+    t_upload = time.perf_counter() - t0
+    scene_bytes = int(gpu.rt_gpu_scene_device_bytes(scene_ref))
+
+    accum = torch.zeros(H * W * 3, dtype=torch.float32, device=dev)
+    pixels = torch.zeros(H * W * 3, dtype=torch.uint8, device=dev)
+    counters = torch.zeros(8, dtype=torch.int64, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream()
+    sptr = C.c_void_p(stream.cuda_stream)
+    launches = {"n": 0}
+    kernel_events = []
+
+    def step(timed: bool):
+        flush.zero_()                                              # L2 flush between steps
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record(stream)
+        a, first = s_begin, True
+        while a < s_end:
+            b = min(a + slice_spp, s_end)
+            gpu_check(gpu.rt_gpu_render_accum_device(scene_ref, W, H, a, b, B, 0, 0 if first else 1, accum.data_ptr(),
+                                                     None, None, counters.data_ptr() if timed else None, sptr))
+            launches["n"] += 1
+            a, first = b, False
+        k1.record(stream)
+        if timed:
+            kernel_events.append((k0, k1, (s_end - s_begin + slice_spp - 1) // slice_spp))
+        if world > 1:
+            dist.reduce(accum, dst=0, op=dist.ReduceOp.SUM)        # NCCL over NVLink: 24.9 MB f32
+        if rank == 0:
+            gpu_check(gpu.rt_gpu_resolve_device(accum.data_ptr(), W, H, SPP, pixels.data_ptr(), W, 3, sptr))
+            launches["n"] += 1
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step(False)
+    barrier()
+    launches["n"] = 0
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step(True)
+    e1.record(stream)
+    barrier()
+    clocks = sampler.finish()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms.item())
+    ms_per_step = total_ms / args.steps
+    value = W * H * SPP / (ms_per_step * 1e-3) / 1e6
+
+    # dominant kernel: rt_render_kernel, averaged over this rank's timed launches
+    kern_ms = sum(a.elapsed_time(b) for a, b, _ in kernel_events)
+    n_kern = sum(n for _, _, n in kernel_events)
+    ctr = dict(zip(COUNTER_NAMES, [int(v) for v in counters.cpu().tolist()]))
+    flops_per_launch = algorithmic_flops(ctr) / max(n_kern, 1)
+    achieved_tflops = flops_per_launch / (kern_ms / max(n_kern, 1) * 1e-3) / 1e12
+    peak_ops = float(gpu.rt_gpu_measure_fp32_issue())
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "dram_traffic.json")
+    if os.path.exists(prof):
+        try:
+            traffic = json.load(open(prof)).get("rt_render_kernel_bytes_per_launch")
+        except Exception:
+            traffic = None
+    cache_bytes = (BYTES_NODE * ctr["nodes"] + BYTES_LEAF * ctr["leaves"] + BYTES_ACCEPT * ctr["accepts"] +
+                   BYTES_SHADE * ctr["shades"]) / max(n_kern, 1)
+    roofline = {"kernel": "rt_render_kernel", "bound": "fp32_issue (not hbm, not tensor: SURVEY 8d)",
+                "achieved": round(achieved_tflops, 3), "peak": round(peak_ops / 1e12, 3), "unit": "TFLOP/s",
+                "frac": round(achieved_tflops / (peak_ops / 1e12), 4) if peak_ops else None, "traffic": traffic,
+                "peak_source": "measured live: non-fused FMUL+FADD issue rate (csrc/rt_peak.cu); MEASURED_PEAKS.json has no FP32 entry",
+                "flop_model": "SURVEY 8d: 40/sample + 200/node + 456/leaf + 33/accept + 700/shade + 90/miss, from the kernel's own counters",
+                "flops_per_launch": flops_per_launch, "launch_ms": round(kern_ms / max(n_kern, 1), 4),
+                "cache_level_bytes_per_launch": cache_bytes,
+                "hbm_compulsory_bytes_per_launch": scene_bytes + 2 * W * H * 12,
+                "per_sample": {k: round(ctr[k] / max(ctr["samples"], 1), 3) for k in ("rays", "nodes", "leaves", "shades", "misses")}}
+
+    # ---- e2e: through render_thread_proc with HOST buffers (N=1), or its device-level pieces + NCCL (N>1)
+    host_pixels = np.zeros((H, W, 3), dtype=np.uint8)
+    pinned = torch.empty(H * W * 3, dtype=torch.uint8).pin_memory()
+    e2e_steps = max(1, min(args.steps, 2))
+
+    def e2e_step():
+        gpu_check(gpu.rt_gpu_scene_upload(scene_ref))              # H2D: nodes, triangles, textures, environment
+        if world == 1:
+            driver.set_options(slice_samples=slice_spp)
+            driver.render(loaded, W, H, SPP, B, n_threads=1, out=host_pixels)   # D2H inside
+        else:
+            step(False)
+            if rank == 0:
+                pinned.copy_(pixels, non_blocking=True)
+            torch.cuda.synchronize()
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = W * H * SPP / float(e2e_s.item()) / 1e6
+
+    if rank == 0:
+        cpu, cpu_spp, cpu_dt = (None, None, None)
+        if world == 1 and not args.no_cpu:
+            cpu, cpu_spp, cpu_dt = cpu_reference_rate(args)
+        t0 = time.perf_counter()
+        driver.save_image("/tmp/bench_helmet.png", host_pixels if world == 1 else pinned.numpy().reshape(H, W, 3))
+        t_save = time.perf_counter() - t0
+        line = {"metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": dict(workload_config(args, f"spp-range split x{world}, NCCL reduce(sum) of the f32 accumulator to rank 0"),
+                               l2="flushed between steps (256 MiB memset inside the timed region, ~0.05 ms)",
+                               slice_spp=slice_spp),
+                "clocks": clocks, "gpu_launches": launches["n"],
+                "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": scene_bytes,
+                        "d2h_bytes_per_step": W * H * 3,
+                        "how": "rt_gpu_scene_upload + render_thread_proc(host Image) per step" if world == 1 else
+                               "scene upload + per-rank render + NCCL reduce + resolve + D2H to pinned host on rank 0"},
+                "roofline": roofline, "cpu_baseline": cpu,
+                "time_to_image_s": {"load_decode_bvh": round(t_load, 3), "upload": round(t_upload, 3),
+                                    "render_e2e": round(float(e2e_s.item()), 3), "png_encode": round(t_save, 3)}}
+        print(json.dumps(line), flush=True)
+    loaded.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--spp", type=int, default=1024)
+    ap.add_argument("--bounces", type=int, default=8)
+    ap.add_argument("--slice", type=int, default=32, help="samples per kernel launch")
+    ap.add_argument("--cpu-spp", type=int, default=4, help="--impl reference: spp of each bounded CPU step")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    import __graft_entry__ as entry
+    if not (os.path.exists(os.path.join(ROOT, "raytracing_c_b200", "csrc", "libraytracer_gpu.so"))
+            and os.path.exists(os.path.join(ROOT, "oracle", "liboracle.so"))):
+        entry.build()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

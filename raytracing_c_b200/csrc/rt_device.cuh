@@ -1,0 +1,85 @@
+// rt_device.cuh — device-side data layout and small vector helpers.
+//
+// HBM layout (uploaded once per Scene, see rt_cabi.cu):
+//   nodes     f32[n_nodes][6][8]   exactly the host BVH_Node bytes (192 B): row r of
+//                                  node n is one 32-byte sector, lane j of an octet
+//                                  reads child j's bound -> 6 sector loads per visit.
+//   leaf_pos  f32[n_leaves][9][8]  the host's nine strided SoA arrays regrouped
+//                                  leaf-major (288 B contiguous per leaf instead of
+//                                  9 lines N*4 bytes apart); rows x0 x1 x2 y0 y1 y2 z0 z1 z2.
+//   tri_rec   float4[n_slots][7]   shading record (112 B): geometric normal, three
+//                                  vertex normals, tangent, bitangent, three UVs,
+//                                  material index (Triangle_AOS with the Shader
+//                                  function pointer replaced by a table index).
+//   materials, textures            PBR_Shader_Data with Image* -> texture slot;
+//                                  texels repacked RGB8 -> RGBA8 (one 32-bit load per tap).
+// Everything is read-only during a render and small enough (<= ~75 MB with the
+// helmet's four 2048^2 textures) to live in the 126 MB L2.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "rt_math.h"
+#include "rt_seed.h"
+
+#define RT_EPS 0.0001f
+#define RT_MAX_DEPTH 8
+
+struct V3 { float x, y, z; };
+
+struct TextureDev {
+  const uchar4 *texels;
+  int width, height;
+};
+
+struct MaterialDev {
+  float base[3], emission[3];
+  float roughness, metalness, normal_strength, sheen, sheen_tint, aniso;
+  int   tex_albedo, tex_normal, tex_mr, tex_emission;   // -1 = none
+};
+
+struct SceneDev {
+  const float       *nodes;
+  const float       *leaf_pos;
+  const float4      *tri_rec;
+  const MaterialDev *materials;
+  const TextureDev  *textures;
+  int                env_texture;
+  int                depth, n_internal, n_slots;
+  float              view[3][4];      // rows 0..2 of the camera-to-world matrix
+  float              focal_length;
+};
+
+struct RenderParams {
+  SceneDev  scene;
+  int       width, height;
+  int       sample_begin, sample_end, max_bounces;
+  uint32_t  user_seed;
+  int       accumulate;
+  float    *accum;
+  float    *per_sample;
+  int      *hit_ids;
+  unsigned long long *counters;
+  unsigned int       *job_counter;
+};
+
+__device__ __forceinline__ V3 mk3(float x, float y, float z) { V3 v; v.x = x; v.y = y; v.z = z; return v; }
+__device__ __forceinline__ V3 add3(V3 a, V3 b)   { return mk3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ V3 sub3(V3 a, V3 b)   { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ V3 mul3(V3 a, V3 b)   { return mk3(a.x * b.x, a.y * b.y, a.z * b.z); }
+__device__ __forceinline__ V3 scale3(V3 a, float s) { return mk3(a.x * s, a.y * s, a.z * s); }
+// left-to-right sum, products rounded separately (built with -fmad=false)
+__device__ __forceinline__ float dot3(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ V3 cross3(V3 a, V3 b) {
+  return mk3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+__device__ __forceinline__ V3 normalize3(V3 a) {
+  float inv = 1.0f / __fsqrt_rn(dot3(a, a));
+  return scale3(a, inv);
+}
+__device__ __forceinline__ float lerp1(float a, float b, float t) { return a * (1 - t) + b * t; }
+__device__ __forceinline__ V3 lerp3(V3 a, V3 b, float t) { return mk3(lerp1(a.x, b.x, t), lerp1(a.y, b.y, t), lerp1(a.z, b.z, t)); }
+__device__ __forceinline__ float sel_min(float a, float b) { return a < b ? a : b; }   // MINPS: b when unordered
+__device__ __forceinline__ float sel_max(float a, float b) { return a > b ? a : b; }   // MAXPS: b when unordered
+__device__ __forceinline__ float clamp1(float x, float lo, float hi) { return x < lo ? lo : (x > hi ? hi : x); }

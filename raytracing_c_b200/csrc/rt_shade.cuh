@@ -1,0 +1,225 @@
+// rt_shade.cuh — per-lane shading: manual bilinear texture fetch, equirect
+// environment lookup, normal mapping and the Disney-style diffuse + GGX-VNDF
+// specular + sheen sampler.
+//
+// Behavioural contract (operation order included — results must equal the CPU
+// oracle bit for bit): reference driver.c:49-104 (sampler, environment),
+// :118-183 (hemisphere sample, normal map, frame, sheen), :200-348 (BRDF),
+// :350-409 (material fetch and glue); common.h:82-88 (sRGB decode by pow only,
+// AFTER filtering).  The reference reaches this code through a host function
+// pointer per triangle; here it is a direct call with a material-table index.
+// f32/f64 promotions follow the reference's literals (driver.c:119,214,220,
+// 238,241-246,263,313): PI is a double.
+#pragma once
+
+#include "rt_device.cuh"
+
+struct ShadeIn  { V3 dir, normal, normal_geo, tangent, bitangent; float u, v; };
+struct ShadeOut { V3 dir, tint, emission; bool terminate; };
+
+__device__ __forceinline__ float rnd(uint32_t &state) { return rt_rand_f32(&state); }
+
+__device__ __forceinline__ V3 texel_rgb(const TextureDev &tex, int x, int y) {
+  uchar4 t = __ldg(&tex.texels[x + tex.width * y]);
+  return mk3((float)t.x / 255.999f, (float)t.y / 255.999f, (float)t.z / 255.999f);
+}
+
+// driver.c:49-93: negative wrap, fract, no half-texel offset, +1 neighbour clamped
+__device__ __noinline__ V3 sample_bilinear(const TextureDev &tex, float u, float v) {
+  if (u < 0) u += (float)(-(int)u + 1);
+  if (v < 0) v += (float)(-(int)v + 1);
+  u = u - floorf(u);
+  v = v - floorf(v);
+  float px = u * (float)tex.width;
+  float py = v * (float)tex.height;
+  int x0 = (int)px, y0 = (int)py;
+  float a = px - (float)x0, b = py - (float)y0;
+  int x1 = (x0 + 1 < tex.width)  ? x0 + 1 : x0;
+  int y1 = (y0 + 1 < tex.height) ? y0 + 1 : y0;
+  V3 top = lerp3(texel_rgb(tex, x0, y0), texel_rgb(tex, x1, y0), a);
+  V3 bot = lerp3(texel_rgb(tex, x0, y1), texel_rgb(tex, x1, y1), a);
+  return lerp3(top, bot, b);
+}
+
+// common.h:82-88
+__device__ __forceinline__ V3 decode_srgb(V3 c) {
+  return mk3(rt_powf((c.x + 0.055f) / 1.055f, 2.4f),
+             rt_powf((c.y + 0.055f) / 1.055f, 2.4f),
+             rt_powf((c.z + 0.055f) / 1.055f, 2.4f));
+}
+
+// driver.c:95-104 (asin argument clamped: DESIGN.md deviation list)
+__device__ __noinline__ V3 environment(const SceneDev &sc, V3 dir) {
+  float inv_pi     = (float)(1.0f / RT_PI);
+  float inv_two_pi = (float)(1.0f / (2.0f * RT_PI));
+  float u = 0.5f + rt_atan2f(dir.z, dir.x) * inv_two_pi;
+  float v = 0.5f - rt_asinf(clamp1(dir.y, -1.0f, 1.0f)) * inv_pi;
+  return decode_srgb(sample_bilinear(sc.textures[sc.env_texture], u, v));
+}
+
+__device__ __forceinline__ float luma(V3 c) { return dot3(c, mk3(0.2126f, 0.7152f, 0.0722f)); }
+
+// driver.c:204-210
+__device__ __forceinline__ float schlick1(float f0, float f90, float c) { return f0 + (f90 - f0) * rt_powf(1 - c, 5); }
+
+// driver.c:212-215
+__device__ __forceinline__ float ggx_d(float roughness, float n_h, float k) {
+  float a2 = roughness * roughness;
+  return (float)(a2 / (RT_PI * rt_powf((n_h * n_h) * (a2 * a2 - 1) + 1, k)));
+}
+
+// driver.c:217-221
+__device__ __forceinline__ float smith_g1(float n_v, float alpha2) {
+  float a = alpha2 * alpha2;
+  float b = n_v * n_v;
+  return (float)((2.0 * n_v) / (n_v + __fsqrt_rn(a + b - a * b)));
+}
+
+// driver.c:118-127
+__device__ __forceinline__ V3 cosine_hemisphere(uint32_t &rng) {
+  float angle  = (float)(rnd(rng) * 2 * RT_PI);
+  float radius = __fsqrt_rn(rnd(rng));
+  V3 d;
+  d.x = rt_sinf(angle) * radius;
+  d.y = rt_cosf(angle) * radius;
+  d.z = __fsqrt_rn(1 - radius * radius);
+  return d;
+}
+
+// driver.c:230-250
+__device__ __forceinline__ V3 sample_vndf(V3 V, float ax, float ay, uint32_t &rng) {
+  V3 Vh = normalize3(mk3(ax * V.x, ay * V.y, V.z));
+  float lensq = Vh.x * Vh.x + Vh.y * Vh.y;
+  V3 T1 = lensq > 0 ? scale3(mk3(-Vh.y, Vh.x, 0), 1.0f / __fsqrt_rn(lensq)) : mk3(1, 0, 0);
+  V3 T2 = cross3(Vh, T1);
+
+  float r   = __fsqrt_rn(rnd(rng));
+  float phi = (float)(2.0 * RT_PI * rnd(rng));
+  float t1  = r * rt_cosf(phi);
+  float t2  = r * rt_sinf(phi);
+  float s   = (float)(0.5 * (1.0 + Vh.z));
+  t2        = (float)((1.0 - s) * __fsqrt_rn((float)(1.0 - t1 * t1)) + s * t2);
+
+  double rem = 1.0 - t1 * t1 - t2 * t2;
+  float  h   = __fsqrt_rn((float)(0.0 > rem ? 0.0 : rem));
+  V3 Nh = add3(add3(scale3(T1, t1), scale3(T2, t2)), scale3(Vh, h));
+  return normalize3(mk3(ax * Nh.x, ay * Nh.y, (0.0 > Nh.z ? 0.0f : Nh.z)));
+}
+
+// driver.c:166-183
+__device__ __forceinline__ V3 sheen_term(float sheen, V3 base, float sheen_tint, float h_dot_l) {
+  if (sheen <= 0.0f) return mk3(0, 0, 0);
+  float lum = dot3(mk3(0.3f, 0.6f, 1.0f), base);
+  V3 tint = (lum > 0.0f) ? scale3(base, 1.0f / lum) : mk3(1, 1, 1);
+  float m = 1 - h_dot_l;
+  float w = m * m * m * m * m;
+  return scale3(lerp3(mk3(1, 1, 1), tint, sheen_tint), sheen * w);
+}
+
+// driver.c:350-409 with :287-348 inlined
+__device__ __noinline__ void shade_pbr(const SceneDev &sc, int material, const ShadeIn &in, uint32_t &rng, ShadeOut &out) {
+  const MaterialDev &mat = sc.materials[material];
+
+  // driver.c:129-153
+  V3 n = in.normal;
+  if (mat.tex_normal >= 0) {
+    V3 s = sample_bilinear(sc.textures[mat.tex_normal], in.u, in.v);
+    s = add3(scale3(s, 2.0f), mk3(-1, -1, -1));
+    s.y *= -1;
+    V3 t = in.tangent, b = in.bitangent;
+    float k = mat.normal_strength;
+    n = normalize3(mk3(k * (s.x * t.x + s.y * b.x + s.z * n.x) + n.x * (1 - k),
+                       k * (s.x * t.y + s.y * b.y + s.z * n.y) + n.y * (1 - k),
+                       k * (s.x * t.z + s.y * b.z + s.z * n.z) + n.z * (1 - k)));
+  }
+
+  V3 base = mk3(mat.base[0], mat.base[1], mat.base[2]);
+  if (mat.tex_albedo >= 0) base = mul3(base, decode_srgb(sample_bilinear(sc.textures[mat.tex_albedo], in.u, in.v)));
+
+  float roughness = mat.roughness, metalness = mat.metalness;
+  if (mat.tex_mr >= 0) {
+    V3 mr = sample_bilinear(sc.textures[mat.tex_mr], in.u, in.v);
+    roughness *= mr.y;
+    metalness *= mr.z;
+  }
+  roughness = clamp1(roughness, 0.001f, 1);
+  if (metalness > 0.9f) metalness = 0.9f;
+  metalness /= 0.9f;
+
+  V3 glow = mk3(mat.emission[0], mat.emission[1], mat.emission[2]);
+  if (mat.tex_emission >= 0) glow = mul3(glow, decode_srgb(sample_bilinear(sc.textures[mat.tex_emission], in.u, in.v)));
+  out.emission = glow;
+  out.terminate = false;
+  out.tint = mk3(0, 0, 0);
+
+  // driver.c:155-164
+  V3 t, b;
+  if (fabsf(dot3(n, in.dir)) < 0.9999f)             t = normalize3(cross3(n, in.dir));
+  else if (fabsf(dot3(n, mk3(0, 1, 0))) < 0.9999f)  t = normalize3(cross3(n, mk3(0, 1, 0)));
+  else                                              t = normalize3(cross3(n, mk3(1, 0, 0)));
+  b = cross3(n, t);
+
+  V3 minus_d = scale3(in.dir, -1);
+  V3 wi = mk3(dot3(t, minus_d), dot3(b, minus_d), dot3(n, minus_d));
+
+  // driver.c:287-348
+  float aniso2  = mat.aniso * mat.aniso;
+  float alpha_x = lerp1(roughness * roughness, 1, aniso2);
+  float alpha_y = roughness * roughness;
+  V3 h = sample_vndf(wi, alpha_x, alpha_y, rng);
+
+  V3 f0 = lerp3(mk3(0.04f, 0.04f, 0.04f), base, metalness);
+  float f90 = sel_min(1.0f, (1.0f / 0.04f) * luma(f0));
+  V3 F = add3(f0, scale3(sub3(mk3(f90, f90, f90), f0), rt_powf(1 - dot3(wi, h), 5)));
+
+  float w_diff = 1 - metalness;
+  float w_spec = luma(F);
+  float inv_w  = 1 / (w_diff + w_spec);
+  w_diff *= inv_w;
+  w_spec *= inv_w;
+
+  V3 wo;
+  float fx = 0, fy = 0, fz = 0, fw = 0;
+  if (rnd(rng) < w_diff) {
+    wo = cosine_hemisphere(rng);
+    h = normalize3(add3(wo, wi));
+    float n_l = wo.z, n_v = wi.z;
+    if (!(n_l <= 0 || n_v <= 0)) {
+      float l_h = dot3(wo, h);
+      float pdf = (float)(n_l / RT_PI);
+      float fd90 = 0.5f + 2 * roughness * l_h * l_h;
+      float fa = schlick1(1.0f, fd90, n_l);
+      float fb = schlick1(1.0f, fd90, n_v);
+      V3 diff = scale3(base, (float)(fa * fb / RT_PI));
+      diff = mul3(diff, sub3(mk3(1, 1, 1), F));
+      diff = add3(diff, sheen_term(mat.sheen, base, mat.sheen_tint, l_h));
+      fx = diff.x * n_l; fy = diff.y * n_l; fz = diff.z * n_l;
+      fw = w_diff * pdf;
+    }
+  } else {
+    V3 mwi = scale3(wi, -1);
+    wo = sub3(mwi, scale3(h, 2.0f * dot3(mwi, h)));
+    float n_l = wo.z, n_v = wi.z;
+    if (!(n_l <= 0 || n_v <= 0)) {
+      n_l = sel_max(n_l, 0.001f);
+      n_v = sel_max(n_v, 0.001f);
+      float n_h = sel_min(h.z, 0.99f);
+      float a2  = roughness * roughness;
+      float pdf = (ggx_d(roughness, n_h, 2) * smith_g1(n_v, a2)) / sel_max(0.00001f, 4.0f * n_v);
+      float D = ggx_d(roughness, n_h, 2);
+      float G = smith_g1(n_v, a2) * smith_g1(n_l, a2);
+      V3 spec = scale3(F, D * G / (4 * n_l * n_v));
+      fx = spec.x * n_l; fy = spec.y * n_l; fz = spec.z * n_l;
+      fw = w_spec * pdf;
+    }
+  }
+  // the early `return vec4(0)` paths at driver.c:309-311,328-330 skip the final
+  // normalize; the direction is unused then because the path terminates
+  wo = normalize3(wo);
+
+  out.dir = mk3(t.x * wo.x + b.x * wo.y + n.x * wo.z,
+                t.y * wo.x + b.y * wo.y + n.y * wo.z,
+                t.z * wo.x + b.z * wo.y + n.z * wo.z);
+  if (fw > 0) out.tint = mk3(fx / fw, fy / fw, fz / fw);
+  else        out.terminate = true;
+}

@@ -1,0 +1,199 @@
+"""GPU parity tests: the sm_100a path, called through the C ABI, against the CPU oracle.
+
+Bar (BASELINE.json north_star): BVH layout and primary-hit slots bit-exact; per-pixel radiance
+with identical per-(pixel,sample) RNG streams within 1e-3 relative — here it is asserted EXACT
+(0 ulp) because both sides share rt_math.h and run without FMA contraction; the u8 film and the
+denoiser output byte-exact.  Sizes are chosen so the oracle finishes in seconds.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_ffi
+from raytracing_c_b200 import driver, gpu_lib
+from raytracing_c_b200._ffi import gpu_check
+
+pytestmark = pytest.mark.gpu
+
+MODELS = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "assets", "models")
+
+# Camera overrides recorded in DESIGN.md: the default camera sits
+# inside quad.obj's plane and inside tower.obj's footprint.
+CAMERAS = {
+    "quad.obj": dict(eye=(3.0, 0.0, 0.0), target=(0.0, 0.0, 0.0)),
+    "tower.obj": dict(eye=(0.0, 12.5, 40.0), target=(0.0, 12.5, 0.0)),
+}
+
+
+def load(name, **material_override):
+    cam = driver.look_at(**CAMERAS[name]) if name in CAMERAS else None
+    loaded = driver.load_scene(os.path.join(MODELS, name), shader_proc=oracle_ffi.shader_proc(),
+                               background_proc=oracle_ffi.background_proc(), camera=cam)
+    for i in range(loaded.model.n_materials):
+        for key, value in material_override.items():
+            setattr(loaded.model.materials[i], key, value)
+    return loaded
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _gpu():
+    gpu_check(gpu_lib().rt_gpu_init(0))
+    yield
+    driver.set_options()
+
+
+def gpu_render(loaded, w, h, spp, bounces=8, n_threads=1, **options):
+    driver.set_options(keep_hit_ids=True, **options)
+    pixels = driver.render(loaded, w, h, spp, bounces, n_threads=n_threads)
+    return dict(pixels=pixels, accum=driver.read_accum(w, h), hit_ids=driver.read_hit_ids(w, h),
+                counters=driver.read_counters())
+
+
+@pytest.mark.parametrize("name", ["quad.obj", "fov_test.obj"])
+def test_primary_hit_ids_bit_exact_1024(name):
+    """BASELINE config 2: 1024x1024, 1 spp, slot ids (raytracer.c:162) identical to the oracle."""
+    loaded = load(name)
+    try:
+        got = gpu_render(loaded, 1024, 1024, 1)
+        ref = oracle_ffi.render(loaded, 1024, 1024, 1, n_threads=8, want_hit_ids=True)
+        assert (ref["hit_ids"] >= 0).sum() > 1000, "camera must see the model"
+        assert np.array_equal(got["hit_ids"], ref["hit_ids"])
+        assert np.array_equal(got["accum"], ref["accum"])
+        assert np.array_equal(got["pixels"], ref["pixels"])
+    finally:
+        loaded.close()
+
+
+@pytest.mark.parametrize("name,w,h,spp", [
+    ("spheres.glb", 256, 256, 16),      # config 1 at reduced resolution
+    ("helmet.glb", 240, 136, 8),        # config 3 aspect, textured PBR + normal map + emission
+    ("tower.obj", 192, 108, 8),         # config 5 aspect
+    ("sheen.glb", 128, 128, 8),
+])
+def test_radiance_exact_vs_oracle(name, w, h, spp):
+    loaded = load(name)
+    try:
+        got = gpu_render(loaded, w, h, spp)
+        ref = oracle_ffi.render(loaded, w, h, spp, n_threads=8, want_hit_ids=True)
+        assert np.array_equal(got["hit_ids"], ref["hit_ids"])
+        assert not np.isnan(ref["accum"]).any()
+        rel = np.abs(got["accum"] - ref["accum"]) / np.maximum(np.abs(ref["accum"]), 1e-6)
+        assert rel.max() <= 1e-3, f"north-star tolerance violated: {rel.max()}"
+        assert np.array_equal(got["accum"], ref["accum"]), "radiance is expected to be bit-identical"
+        assert np.array_equal(got["pixels"], ref["pixels"])
+        assert got["counters"] == ref["counters"], "work counters (rays, node/leaf visits, shades) differ"
+    finally:
+        loaded.close()
+
+
+@pytest.mark.parametrize("sheen_tint", [0.0, 1.0])
+def test_sheen_injected_and_denoised(sheen_tint):
+    """BASELINE config 4: sheen.glb carries no KHR_materials_sheen, so sheen is injected."""
+    loaded = load("sheen.glb", sheen=1.0, sheen_tint=sheen_tint)
+    plain = load("sheen.glb")
+    try:
+        w = h = 160
+        got = gpu_render(loaded, w, h, 8)
+        ref = oracle_ffi.render(loaded, w, h, 8, n_threads=8)
+        base = oracle_ffi.render(plain, w, h, 8, n_threads=8)
+        assert not np.array_equal(ref["accum"], base["accum"]), "the sheen lobe must change the image"
+        assert np.array_equal(got["accum"], ref["accum"])
+        assert np.array_equal(got["pixels"], ref["pixels"])
+        assert np.array_equal(driver.denoise(got["pixels"]), oracle_ffi.denoise(ref["pixels"]))
+    finally:
+        loaded.close()
+        plain.close()
+
+
+def test_anisotropic_material():
+    loaded = load("spheres.glb", anisotropic_strength=0.7)
+    try:
+        got = gpu_render(loaded, 128, 128, 4)
+        ref = oracle_ffi.render(loaded, 128, 128, 4, n_threads=8)
+        assert np.array_equal(got["accum"], ref["accum"])
+    finally:
+        loaded.close()
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (7, 5), (33, 31), (64, 64), (257, 130)])
+def test_denoiser_byte_exact_random(shape):
+    h, w = shape
+    rng = np.random.default_rng(h * 1000 + w)
+    img = rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8)
+    # smooth regions + salt noise so both blend branches are exercised
+    img[: h // 2] = (img[: h // 2] // 32) * 32
+    assert np.array_equal(driver.denoise(img), oracle_ffi.denoise(img))
+
+
+def test_denoiser_constant_and_ties():
+    img = np.full((40, 50, 3), 128, dtype=np.uint8)
+    img[10, 10] = (255, 255, 255)
+    img[20:30, 20:30] = (0, 0, 0)
+    assert np.array_equal(driver.denoise(img), oracle_ffi.denoise(img))
+
+
+def test_ragged_sizes_and_threads():
+    """Width/height not multiples of the 8x4 job tile or the 32x32 chunk; several host threads
+    enter render_thread_proc with one context (driver.c:801-803)."""
+    loaded = load("fov_test.obj")
+    try:
+        for (w, h) in [(1, 1), (13, 7), (100, 37)]:
+            got = gpu_render(loaded, w, h, 3, n_threads=4)
+            ref = oracle_ffi.render(loaded, w, h, 3, n_threads=3)
+            assert np.array_equal(got["accum"], ref["accum"])
+            assert np.array_equal(got["pixels"], ref["pixels"])
+    finally:
+        loaded.close()
+
+
+def test_sample_slices_accumulate_in_order():
+    """Slicing the sample range over several launches keeps the f32 sum sequential, hence identical."""
+    loaded = load("spheres.glb")
+    try:
+        a = gpu_render(loaded, 96, 96, 24, slice_samples=24)
+        b = gpu_render(loaded, 96, 96, 24, slice_samples=5)
+        assert np.array_equal(a["accum"], b["accum"])
+        ref = oracle_ffi.render(loaded, 96, 96, 24, n_threads=8)
+        assert np.array_equal(a["accum"], ref["accum"])
+    finally:
+        loaded.close()
+
+
+def test_sample_range_split_matches_sum():
+    """The multi-GPU split: ranks render disjoint sample ranges; the sum of the partial accumulators
+    equals the full render up to f32 addition order."""
+    loaded = load("spheres.glb")
+    try:
+        w = h = 96
+        full = gpu_render(loaded, w, h, 16)["accum"]
+        lo = gpu_render(loaded, w, h, 16, sample_begin=0, sample_end=8)["accum"]
+        hi = gpu_render(loaded, w, h, 16, sample_begin=8, sample_end=16)["accum"]
+        ref_hi = oracle_ffi.render(loaded, w, h, 16, n_threads=8, sample_begin=8, sample_end=16)["accum"]
+        assert np.array_equal(hi, ref_hi)
+        np.testing.assert_allclose(lo + hi, full, rtol=1e-5, atol=1e-6)
+    finally:
+        loaded.close()
+
+
+def test_max_bounces_and_seed():
+    loaded = load("spheres.glb")
+    try:
+        for bounces, seed in [(1, 0), (2, 7), (8, 12345)]:
+            got = gpu_render(loaded, 80, 60, 4, bounces=bounces, user_seed=seed)
+            ref = oracle_ffi.render(loaded, 80, 60, 4, max_bounces=bounces, n_threads=8, user_seed=seed)
+            assert np.array_equal(got["accum"], ref["accum"])
+    finally:
+        loaded.close()
+
+
+def test_unregistered_shader_is_an_error():
+    loaded = driver.load_scene(os.path.join(MODELS, "quad.obj"), shader_proc=0xDEAD0, background_proc=oracle_ffi.background_proc())
+    try:
+        import ctypes
+        gpu_lib().rt_gpu_register_background(oracle_ffi.background_proc())
+        rc = gpu_lib().rt_gpu_scene_upload(ctypes.byref(loaded.scene))
+        assert rc != 0
+        assert b"not registered" in gpu_lib().rt_gpu_last_error()
+    finally:
+        loaded.close()
