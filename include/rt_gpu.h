@@ -68,7 +68,7 @@ int rt_gpu_last_launches(void);                        /* kernels launched by th
 f64 rt_gpu_last_kernel_ms(void);                       /* CUDA-event time of the last call's trace kernels */
 
 /* ---- device-pointer level (all pointers are device memory; stream is a
- *      cudaStream_t passed as void*, NULL = the library's stream) ---- */
+ *      cudaStream_t passed as void*, NULL = the legacy default stream) ---- */
 int rt_gpu_render_accum_device(Scene const *scene, isize width, isize height,
                                isize sample_begin, isize sample_end, isize max_bounces,
                                u32 user_seed, i32 accumulate,

@@ -1,0 +1,2 @@
+/* TEST INFRASTRUCTURE: part of the Codin stand-in, see codin.h */
+#include "codin.h"

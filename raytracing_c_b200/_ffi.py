@@ -13,7 +13,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 HOST_LIB = os.path.join(HERE, "host", "librt_host.so")
-GPU_LIB = os.path.join(HERE, "csrc", "libraytracer_gpu.so")
+GPU_LIB = os.environ.get("RT_GPU_LIB", os.path.join(HERE, "csrc", "libraytracer_gpu.so"))   # override: kernel experiments only
 
 isize = C.c_ssize_t
 

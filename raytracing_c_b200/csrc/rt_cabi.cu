@@ -383,7 +383,7 @@ int rt_gpu_render_accum_device(Scene const *scene, isize width, isize height, is
   std::lock_guard<std::mutex> lock(g_mutex);
   return render_device_locked(scene, width, height, sample_begin, sample_end, max_bounces, user_seed, accumulate,
                               d_accum, d_per_sample, d_hit_ids, reinterpret_cast<unsigned long long *>(d_counters),
-                              stream ? static_cast<cudaStream_t>(stream) : g.stream);
+                              static_cast<cudaStream_t>(stream));
 }
 
 int rt_gpu_resolve_device(f32 const *d_accum, isize width, isize height, isize samples, u8 *d_pixels, isize stride,
@@ -391,7 +391,7 @@ int rt_gpu_resolve_device(f32 const *d_accum, isize width, isize height, isize s
   if (ensure_init()) return 1;
   if (samples < 1 || components < 3) return fail("resolve: samples >= 1 and components >= 3 required");
   int e = rt_launch_resolve(d_accum, (int)width, (int)height, (int)samples, d_pixels, (int)stride, components,
-                            stream ? static_cast<cudaStream_t>(stream) : g.stream);
+                            static_cast<cudaStream_t>(stream));
   if (e) return fail("resolve kernel launch failed: %s", cudaGetErrorString((cudaError_t)e));
   g.last_launches++;
   return 0;
@@ -402,7 +402,7 @@ int rt_gpu_denoise_device(u8 const *d_src, u8 *d_dst, isize width, isize height,
   if (ensure_init()) return 1;
   if (d_src == d_dst) return fail("denoise: src and dst must differ (reference denoiser.c:130)");
   int e = rt_launch_denoise(d_src, d_dst, (int)width, (int)height, (int)src_stride, (int)dst_stride, components,
-                            stream ? static_cast<cudaStream_t>(stream) : g.stream);
+                            static_cast<cudaStream_t>(stream));
   if (e) return fail("denoise kernel launch failed: %s", cudaGetErrorString((cudaError_t)e));
   g.last_launches++;
   return 0;

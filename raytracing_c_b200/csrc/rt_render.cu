@@ -31,6 +31,9 @@
 #include "rt_kernels.h"
 
 #define RT_BLOCK 256
+#ifndef RT_MIN_BLOCKS
+#define RT_MIN_BLOCKS 2
+#endif
 
 struct Mailbox {
   float ox, oy, oz, dx, dy, dz;   // in:  ray
@@ -72,7 +75,7 @@ __device__ __forceinline__ unsigned octet_min(unsigned omask, unsigned key) {
   return key;
 }
 
-__global__ void __launch_bounds__(RT_BLOCK)
+__global__ void __launch_bounds__(RT_BLOCK, RT_MIN_BLOCKS)
 rt_render_kernel(const __grid_constant__ RenderParams P) {
   __shared__ Mailbox mail[RT_BLOCK];
   __shared__ float   level_entry[RT_BLOCK / 8][RT_MAX_DEPTH + 1][8];
