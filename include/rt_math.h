@@ -5,9 +5,9 @@
  * common.h:82-92).  glibc and CUDA's libdevice differ from each other by ulps,
  * and one ulp at a lobe-pick or a texel boundary sends a whole path elsewhere.
  * Every function here is built only from IEEE-754 +,-,*,/ and sqrt in binary64
- * plus integer bit moves, so — compiled without FMA contraction
- * (gcc -ffp-contract=off, nvcc -fmad=false) — the CPU oracle and the sm_100a
- * kernels produce bit-identical results.  Accuracy is < 1 ulp of binary32
+ * plus integer bit moves and EXPLICIT fused multiply-adds (RT_FMA), so — compiled
+ * without automatic FMA contraction (gcc -ffp-contract=off, nvcc -fmad=false) —
+ * the CPU oracle and the sm_100a kernels produce bit-identical results.  Accuracy is < 1 ulp of binary32
  * (tests/test_rt_math.py checks against libm), i.e. the same contract a libm
  * gives; the reference's own libm is unpinned (Codin is not in the tree).
  */
@@ -18,8 +18,22 @@
 
 #if defined(__CUDACC__)
 #define RT_HD __host__ __device__ __forceinline__
+/* the f64 bodies stay out of line on the device: inlined at every call site they
+ * pushed the render kernel to 99 KB of SASS, past the instruction cache */
+#define RT_HD_NOINLINE static __host__ __device__ __noinline__
 #else
 #define RT_HD static inline
+#define RT_HD_NOINLINE static inline
+#endif
+
+/* Fused multiply-add, EXPLICIT and identical on both sides (one IEEE rounding):
+ * DFMA on the device, vfmadd on the host (oracle built with -mfma; without the
+ * instruction __builtin_fma falls back to libm's exact software fma).  Automatic
+ * contraction stays off everywhere else. */
+#if defined(__CUDA_ARCH__)
+#define RT_FMA(a, b, c) __fma_rn((a), (b), (c))
+#else
+#define RT_FMA(a, b, c) __builtin_fma((a), (b), (c))
 #endif
 
 #define RT_PI      3.14159265358979323846
@@ -70,15 +84,15 @@ RT_HD double rt_log2_pos(double d) {
   double s  = (m - 1.0) / (m + 1.0);
   double s2 = s * s;
   double p  = 1.0 / 15.0;
-  p = p * s2 + 1.0 / 13.0;
-  p = p * s2 + 1.0 / 11.0;
-  p = p * s2 + 1.0 / 9.0;
-  p = p * s2 + 1.0 / 7.0;
-  p = p * s2 + 1.0 / 5.0;
-  p = p * s2 + 1.0 / 3.0;
-  p = p * s2 + 1.0;
+  p = RT_FMA(p, s2, 1.0 / 13.0);
+  p = RT_FMA(p, s2, 1.0 / 11.0);
+  p = RT_FMA(p, s2, 1.0 / 9.0);
+  p = RT_FMA(p, s2, 1.0 / 7.0);
+  p = RT_FMA(p, s2, 1.0 / 5.0);
+  p = RT_FMA(p, s2, 1.0 / 3.0);
+  p = RT_FMA(p, s2, 1.0);
   /* 2/ln(2) */
-  return (double)e + (s * p) * 2.8853900817779268;
+  return RT_FMA(s * p, 2.8853900817779268, (double)e);
 }
 
 /* 2^t for |t| <= 1000 → double (caller clamps). */
@@ -86,23 +100,23 @@ RT_HD double rt_exp2_f64(double t) {
   double k = rt_floor_f64(t + 0.5);
   double f = (t - k) * 0.6931471805599453;   /* |f| <= 0.3466 */
   double p = 1.0 / 39916800.0;
-  p = p * f + 1.0 / 3628800.0;
-  p = p * f + 1.0 / 362880.0;
-  p = p * f + 1.0 / 40320.0;
-  p = p * f + 1.0 / 5040.0;
-  p = p * f + 1.0 / 720.0;
-  p = p * f + 1.0 / 120.0;
-  p = p * f + 1.0 / 24.0;
-  p = p * f + 1.0 / 6.0;
-  p = p * f + 0.5;
-  p = p * f + 1.0;
-  p = p * f + 1.0;
+  p = RT_FMA(p, f, 1.0 / 3628800.0);
+  p = RT_FMA(p, f, 1.0 / 362880.0);
+  p = RT_FMA(p, f, 1.0 / 40320.0);
+  p = RT_FMA(p, f, 1.0 / 5040.0);
+  p = RT_FMA(p, f, 1.0 / 720.0);
+  p = RT_FMA(p, f, 1.0 / 120.0);
+  p = RT_FMA(p, f, 1.0 / 24.0);
+  p = RT_FMA(p, f, 1.0 / 6.0);
+  p = RT_FMA(p, f, 0.5);
+  p = RT_FMA(p, f, 1.0);
+  p = RT_FMA(p, f, 1.0);
   int64_t ki = (int64_t)k;
   return p * rt_u64_as_f64((uint64_t)(ki + 1023) << 52);
 }
 
 /* powf with C99 special cases for the inputs the path can produce. */
-RT_HD float rt_powf(float x, float y) {
+RT_HD_NOINLINE float rt_powf(float x, float y) {
   if (y == 0.0f) return 1.0f;
   if (x != x || y != y) return x + y;
   float sign = 1.0f;
@@ -126,40 +140,40 @@ RT_HD float rt_powf(float x, float y) {
 RT_HD void rt_sincos_reduce(float x, double *r, int *quadrant) {
   double d = (double)x;
   double q = rt_floor_f64(d * 0.6366197723675814 + 0.5);
-  double a = d - q * 1.5707963267341256;       /* pi/2 high */
-  a = a - q * 6.077100506506192e-11;           /* pi/2 low  */
+  double a = RT_FMA(-q, 1.5707963267341256, d);      /* pi/2 high: q*hi is exact */
+  a = RT_FMA(-q, 6.077100506506192e-11, a);          /* pi/2 low  */
   *r = a;
   *quadrant = (int)((int64_t)q & 3);
 }
 RT_HD double rt_sin_poly(double r) {
   double r2 = r * r;
   double p = 1.0 / 6227020800.0;
-  p = p * r2 - 1.0 / 39916800.0;
-  p = p * r2 + 1.0 / 362880.0;
-  p = p * r2 - 1.0 / 5040.0;
-  p = p * r2 + 1.0 / 120.0;
-  p = p * r2 - 1.0 / 6.0;
-  p = p * r2 + 1.0;
+  p = RT_FMA(p, r2, -1.0 / 39916800.0);
+  p = RT_FMA(p, r2, 1.0 / 362880.0);
+  p = RT_FMA(p, r2, -1.0 / 5040.0);
+  p = RT_FMA(p, r2, 1.0 / 120.0);
+  p = RT_FMA(p, r2, -1.0 / 6.0);
+  p = RT_FMA(p, r2, 1.0);
   return r * p;
 }
 RT_HD double rt_cos_poly(double r) {
   double r2 = r * r;
   double p = 1.0 / 87178291200.0;
-  p = p * r2 - 1.0 / 479001600.0;
-  p = p * r2 + 1.0 / 3628800.0;
-  p = p * r2 - 1.0 / 40320.0;
-  p = p * r2 + 1.0 / 720.0;
-  p = p * r2 - 1.0 / 24.0;
-  p = p * r2 + 0.5;
-  return 1.0 - r2 * p;
+  p = RT_FMA(p, r2, -1.0 / 479001600.0);
+  p = RT_FMA(p, r2, 1.0 / 3628800.0);
+  p = RT_FMA(p, r2, -1.0 / 40320.0);
+  p = RT_FMA(p, r2, 1.0 / 720.0);
+  p = RT_FMA(p, r2, -1.0 / 24.0);
+  p = RT_FMA(p, r2, 0.5);
+  return RT_FMA(-r2, p, 1.0);
 }
-RT_HD float rt_sinf(float x) {
+RT_HD_NOINLINE float rt_sinf(float x) {
   double r; int q;
   rt_sincos_reduce(x, &r, &q);
   double v = (q & 1) ? rt_cos_poly(r) : rt_sin_poly(r);
   return (float)((q & 2) ? -v : v);
 }
-RT_HD float rt_cosf(float x) {
+RT_HD_NOINLINE float rt_cosf(float x) {
   double r; int q;
   rt_sincos_reduce(x, &r, &q);
   double v = (q & 1) ? rt_sin_poly(r) : rt_cos_poly(r);
@@ -167,7 +181,7 @@ RT_HD float rt_cosf(float x) {
 }
 
 /* atan2 in binary64 on finite inputs; one division. */
-RT_HD double rt_atan2_f64(double y, double x) {
+RT_HD_NOINLINE double rt_atan2_f64(double y, double x) {
   int neg_y = (int)(rt_f64_as_u64(y) >> 63);
   int neg_x = (int)(rt_f64_as_u64(x) >> 63);
   double ay = neg_y ? -y : y;
@@ -184,20 +198,20 @@ RT_HD double rt_atan2_f64(double y, double x) {
     else                               { z = mn / mx; }
     double z2 = z * z;
     double p = 1.0 / 27.0;
-    p = 1.0 / 25.0 - p * z2;
-    p = 1.0 / 23.0 - p * z2;
-    p = 1.0 / 21.0 - p * z2;
-    p = 1.0 / 19.0 - p * z2;
-    p = 1.0 / 17.0 - p * z2;
-    p = 1.0 / 15.0 - p * z2;
-    p = 1.0 / 13.0 - p * z2;
-    p = 1.0 / 11.0 - p * z2;
-    p = 1.0 / 9.0  - p * z2;
-    p = 1.0 / 7.0  - p * z2;
-    p = 1.0 / 5.0  - p * z2;
-    p = 1.0 / 3.0  - p * z2;
-    p = 1.0        - p * z2;
-    a = base + z * p;
+    p = RT_FMA(-p, z2, 1.0 / 25.0);
+    p = RT_FMA(-p, z2, 1.0 / 23.0);
+    p = RT_FMA(-p, z2, 1.0 / 21.0);
+    p = RT_FMA(-p, z2, 1.0 / 19.0);
+    p = RT_FMA(-p, z2, 1.0 / 17.0);
+    p = RT_FMA(-p, z2, 1.0 / 15.0);
+    p = RT_FMA(-p, z2, 1.0 / 13.0);
+    p = RT_FMA(-p, z2, 1.0 / 11.0);
+    p = RT_FMA(-p, z2, 1.0 / 9.0);
+    p = RT_FMA(-p, z2, 1.0 / 7.0);
+    p = RT_FMA(-p, z2, 1.0 / 5.0);
+    p = RT_FMA(-p, z2, 1.0 / 3.0);
+    p = RT_FMA(-p, z2, 1.0);
+    a = RT_FMA(z, p, base);
   }
   if (swap)  a = 1.57079632679489662 - a;
   if (neg_x) a = RT_PI - a;

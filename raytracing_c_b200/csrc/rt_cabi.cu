@@ -128,13 +128,22 @@ int build_device_scene(const Scene *scene, DeviceScene &ds) {
   std::vector<float> nodes((size_t)n_nodes * 48);
   memcpy(nodes.data(), scene->bvh.nodes.data, nodes.size() * sizeof(float));
 
+  // leaf-major rows: p0.xyz, e1 = p1 - p0, e2 = p2 - p0.  The two edge vectors are the f32
+  // subtractions the reference redoes for every ray (raytracer.c:116-122); volatile keeps the
+  // host compiler from doing them in any wider type
   std::vector<float> leaf_pos((size_t)n_leaves * 72);
-  const float *rows[9] = { scene->triangles.x[0], scene->triangles.x[1], scene->triangles.x[2],
-                           scene->triangles.y[0], scene->triangles.y[1], scene->triangles.y[2],
-                           scene->triangles.z[0], scene->triangles.z[1], scene->triangles.z[2] };
+  const float *px[3] = { scene->triangles.x[0], scene->triangles.y[0], scene->triangles.z[0] };
+  const float *p1[3] = { scene->triangles.x[1], scene->triangles.y[1], scene->triangles.z[1] };
+  const float *p2[3] = { scene->triangles.x[2], scene->triangles.y[2], scene->triangles.z[2] };
   for (isize leaf = 0; leaf < n_leaves; leaf++)
-    for (int r = 0; r < 9; r++)
-      memcpy(&leaf_pos[(size_t)leaf * 72 + (size_t)r * 8], rows[r] + leaf * 8, 8 * sizeof(float));
+    for (int a = 0; a < 3; a++)
+      for (int j = 0; j < 8; j++) {
+        isize s = leaf * 8 + j;
+        volatile float e1 = p1[a][s] - px[a][s], e2 = p2[a][s] - px[a][s];
+        leaf_pos[(size_t)leaf * 72 + (size_t)(0 + a) * 8 + j] = px[a][s];
+        leaf_pos[(size_t)leaf * 72 + (size_t)(3 + a) * 8 + j] = e1;
+        leaf_pos[(size_t)leaf * 72 + (size_t)(6 + a) * 8 + j] = e2;
+      }
 
   // materials / textures, de-duplicated by host pointer
   std::map<const void *, int> material_index, texture_index;

@@ -6,7 +6,8 @@
 //                                  reads child j's bound -> 6 sector loads per visit.
 //   leaf_pos  f32[n_leaves][9][8]  the host's nine strided SoA arrays regrouped
 //                                  leaf-major (288 B contiguous per leaf instead of
-//                                  9 lines N*4 bytes apart); rows x0 x1 x2 y0 y1 y2 z0 z1 z2.
+//                                  9 lines N*4 bytes apart); rows p0.x p0.y p0.z, then the
+//                                  edges e1 = p1-p0 and e2 = p2-p0 (x y z each).
 //   tri_rec   float4[n_slots][7]   shading record (112 B): geometric normal, three
 //                                  vertex normals, tangent, bitangent, three UVs,
 //                                  material index (Triangle_AOS with the Shader

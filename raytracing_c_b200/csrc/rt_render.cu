@@ -15,11 +15,17 @@
 //   * TRAVERSAL is cooperative: the reference's AVX2 design tests 8 child boxes /
 //     8 triangles per instruction; here an OCTET (8 adjacent lanes) does the same,
 //     one child box or one triangle per lane, with __shfl_xor min-reductions in
-//     place of the horizontal min.  Each octet walks the 8 rays its own lanes own,
-//     one after the other, through a flat state machine (no recursion, no stack:
-//     the tree is a complete 8-ary heap, parent = (n-1)>>3; the per-level entry
-//     distances live in shared memory).  Node rows are 32-byte sectors, so an
-//     octet's 6 loads per box test and 9 per leaf are fully coalesced.
+//     place of the horizontal min.  The warp's (up to) 32 rays sit in a shared-
+//     memory mailbox; each of the 4 octets pulls the next ray from a per-warp
+//     bitmask when it finishes one, so octets stay busy until the mailbox drains.
+//     The walk is a flat state machine (no recursion, no stack): the tree is a
+//     complete 8-ary heap, parent = (n-1)>>3; per-level entry distances live in
+//     shared memory and a bitmask of levels that still hold untried children lets
+//     a pop jump straight to the next useful ancestor.  Box tests / selection run
+//     in one uniform loop body; leaf tests are batched behind it so octets of a
+//     warp execute the long Möller–Trumbore body together instead of serialising
+//     it against box tests.  Node rows are 32-byte sectors, so an octet's 6 loads
+//     per box test and 9 per leaf are fully coalesced.
 //   * SHADING is per lane (rt_shade.cuh), all 32 lanes of the warp active.
 // Arithmetic is IEEE f32 without FMA contraction (-fmad=false) in the reference's
 // operation order: primary-hit slots and radiance equal the CPU oracle bit for bit.
@@ -32,14 +38,11 @@
 
 #define RT_BLOCK 256
 #ifndef RT_MIN_BLOCKS
-#define RT_MIN_BLOCKS 2
+#define RT_MIN_BLOCKS 3
 #endif
-
-struct Mailbox {
-  float ox, oy, oz, dx, dy, dz;   // in:  ray
-  float t, u, v;                  // out: closest hit
-  int   slot;
-};
+#ifndef RT_BATCH_LEAF
+#define RT_BATCH_LEAF 1
+#endif
 
 // raytracer.c:582-594, one lane of hash12x8
 __device__ __forceinline__ float fract1(float v) { return v - floorf(v); }
@@ -52,19 +55,30 @@ __device__ __forceinline__ float hash12(float px, float py) {
   return fract1((a + b + d * 2.0f) * (c + d));
 }
 
-// raytracer.c:190-230 for ONE child box; MINPS/MAXPS operand order kept (sel_min/sel_max)
+// raytracer.c:190-230 for ONE child box.
+// `regular` = all three reciprocal direction components are finite.  Then no product
+// below can be NaN (finite * finite), so MINPS/MAXPS' "second operand when unordered"
+// rule never fires and the hardware FMNMX gives the same value (a zero's sign can
+// differ, but `enter` is >= EPS and `leave` is only compared).  Otherwise the exact
+// operand-order selects are used (0 * inf lanes, raytracer.c:212-225).
 __device__ __forceinline__ float child_entry(const float *__restrict__ row, float ox, float oy, float oz,
-                                             float ix, float iy, float iz, float t_max) {
+                                             float ix, float iy, float iz, float t_max, bool regular) {
   float ax = (__ldg(row +  0) - ox) * ix;
   float ay = (__ldg(row +  8) - oy) * iy;
   float az = (__ldg(row + 16) - oz) * iz;
   float bx = (__ldg(row + 24) - ox) * ix;
   float by = (__ldg(row + 32) - oy) * iy;
   float bz = (__ldg(row + 40) - oz) * iz;
-  float nx = sel_min(ax, bx), ny = sel_min(ay, by), nz = sel_min(az, bz);
-  float fx = sel_max(ax, bx), fy = sel_max(ay, by), fz = sel_max(az, bz);
-  float enter = sel_max(RT_EPS, sel_max(nx, sel_max(ny, nz)));
-  float leave = sel_min(t_max,  sel_min(fx, sel_min(fy, fz)));
+  float enter, leave;
+  if (regular) {
+    enter = fmaxf(RT_EPS, fmaxf(fminf(ax, bx), fmaxf(fminf(ay, by), fminf(az, bz))));
+    leave = fminf(t_max,  fminf(fmaxf(ax, bx), fminf(fmaxf(ay, by), fmaxf(az, bz))));
+  } else {
+    float nx = sel_min(ax, bx), ny = sel_min(ay, by), nz = sel_min(az, bz);
+    float fx = sel_max(ax, bx), fy = sel_max(ay, by), fz = sel_max(az, bz);
+    enter = sel_max(RT_EPS, sel_max(nx, sel_max(ny, nz)));
+    leave = sel_min(t_max,  sel_min(fx, sel_min(fy, fz)));
+  }
   return (enter >= leave) ? CUDART_INF_F : enter;
 }
 
@@ -75,18 +89,32 @@ __device__ __forceinline__ unsigned octet_min(unsigned omask, unsigned key) {
   return key;
 }
 
+struct Shared {
+  float ox[RT_BLOCK], oy[RT_BLOCK], oz[RT_BLOCK], dx[RT_BLOCK], dy[RT_BLOCK], dz[RT_BLOCK];   // in:  rays
+  float t[RT_BLOCK], u[RT_BLOCK], v[RT_BLOCK];                                                 // out: closest hits
+  int   slot[RT_BLOCK];
+  float level_entry[RT_BLOCK / 8][RT_MAX_DEPTH + 1][8];
+  float texel_lut[256];
+  unsigned todo[RT_BLOCK / 32];
+};
+
 __global__ void __launch_bounds__(RT_BLOCK, RT_MIN_BLOCKS)
 rt_render_kernel(const __grid_constant__ RenderParams P) {
-  __shared__ Mailbox mail[RT_BLOCK];
-  __shared__ float   level_entry[RT_BLOCK / 8][RT_MAX_DEPTH + 1][8];
+  __shared__ Shared sh;
 
   const SceneDev &sc = P.scene;
   const int tid   = threadIdx.x;
   const int lane  = tid & 31;
   const int l8    = tid & 7;
-  const int obase = tid & ~7;
+  const int wbase = tid & ~31;
   const unsigned omask = 0xffu << (lane & 24);
-  float *my_levels = &level_entry[tid >> 3][0][l8];
+  float *my_levels = &sh.level_entry[tid >> 3][0][l8];
+  volatile unsigned *todo = &sh.todo[tid >> 5];
+
+  // u8 -> f32 texel table: the same IEEE division the reference does per tap
+  // (driver.c:69-88), done once per block instead of 12 times per bilinear fetch
+  sh.texel_lut[tid] = (float)tid / 255.999f;
+  __syncthreads();
 
   const int   W = P.width, H = P.height;
   const int   tiles_x = (W + 7) >> 3, tiles_y = (H + 3) >> 2;
@@ -152,59 +180,99 @@ rt_render_kernel(const __grid_constant__ RenderParams P) {
 
     // --------------------------------------------------------------------- trace
     if (has_path) {
-      Mailbox &m = mail[tid];
-      m.ox = o.x; m.oy = o.y; m.oz = o.z; m.dx = d.x; m.dy = d.y; m.dz = d.z;
+      sh.ox[tid] = o.x; sh.oy[tid] = o.y; sh.oz[tid] = o.z;
+      sh.dx[tid] = d.x; sh.dy[tid] = d.y; sh.dz[tid] = d.z;
       c_rays++;
     }
+    if (lane == 0) *todo = active;
     __syncwarp();
     {
-      unsigned todo = (active >> (lane & 24)) & 0xffu;   // this octet's rays
-      int   cur = -1, node = 0, level = 0, hit_slot = -1;
+      int   cur = -1, node = 0, level = 0, hit_slot = -1, leaf = -1;
+      unsigned pending = 0;               // levels (bit = level) that still hold untried children
+      bool  need_box = false, regular = true, finished = false;
       float ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 0, ix = 0, iy = 0, iz = 0;
       float hit_t = CUDART_INF_F, hit_u = 0, hit_v = 0, entry = CUDART_INF_F;
 
       for (;;) {
-        if (cur < 0) {
-          if (todo == 0) break;
-          cur = __ffs(todo) - 1;
-          todo &= todo - 1;
-          const Mailbox &m = mail[obase + cur];
-          ox = m.ox; oy = m.oy; oz = m.oz; dx = m.dx; dy = m.dy; dz = m.dz;
-          ix = 1.0f / dx; iy = 1.0f / dy; iz = 1.0f / dz;           // raytracer.c:198-202
-          hit_t = CUDART_INF_F; hit_slot = -1; hit_u = 0; hit_v = 0;
-          node = 0; level = sc.depth;                                  // raytracer.c:501
-          entry = child_entry(sc.nodes + l8, ox, oy, oz, ix, iy, iz, hit_t);
-          c_nodes++;
-        }
-        // raytracer.c:459-472: nearest unvisited child strictly below the current hit
-        unsigned key  = __float_as_uint(entry);          // entry is >= EPS, +inf or NaN: u32 order == f32 order
-        unsigned best = octet_min(omask, key);
-        if (best >= __float_as_uint(hit_t)) {
-          if (node == 0) {                               // ray finished
-            if (l8 == 0) { Mailbox &m = mail[obase + cur]; m.t = hit_t; m.u = hit_u; m.v = hit_v; m.slot = hit_slot; }
-            cur = -1;
+        // ---- uniform part: fetch / box test / select / pop, until this octet holds a leaf to test
+        while (!finished && leaf < 0) {
+          if (cur < 0) {
+            int got = -1;
+            if (l8 == 0) {                               // the octet leader claims the next ray of the warp
+              unsigned seen = *todo;
+              while (seen) {
+                unsigned bit = seen & (0u - seen);
+                unsigned prev = atomicCAS((unsigned *)todo, seen, seen ^ bit);
+                if (prev == seen) { got = __ffs(bit) - 1; break; }
+                seen = prev;
+              }
+            }
+            got = __shfl_sync(omask, got, lane & 24);
+            if (got < 0) { finished = true; break; }
+            cur = wbase + got;
+            ox = sh.ox[cur]; oy = sh.oy[cur]; oz = sh.oz[cur];
+            dx = sh.dx[cur]; dy = sh.dy[cur]; dz = sh.dz[cur];
+            ix = 1.0f / dx; iy = 1.0f / dy; iz = 1.0f / dz;         // raytracer.c:198-202
+            regular = (fabsf(ix) < CUDART_INF_F) & (fabsf(iy) < CUDART_INF_F) & (fabsf(iz) < CUDART_INF_F);
+            hit_t = CUDART_INF_F; hit_slot = -1; hit_u = 0; hit_v = 0;
+            node = 0; level = sc.depth; pending = 0;                   // raytracer.c:501
+            need_box = true;
+          }
+          if (need_box) {
+            entry = child_entry(sc.nodes + (size_t)node * 48 + l8, ox, oy, oz, ix, iy, iz, hit_t, regular);
+            need_box = false;
+            c_nodes++;
+          }
+          // raytracer.c:459-472: nearest unvisited child strictly below the current hit.
+          // entry is >= EPS, +inf or NaN: its u32 order equals its f32 order
+          const unsigned hit_bits = __float_as_uint(hit_t);
+          const unsigned key  = __float_as_uint(entry);
+          const unsigned best = octet_min(omask, key);
+          if (best >= hit_bits) {
+            // nothing left under this node: jump to the nearest ancestor with untried children
+            if (pending == 0) {
+              if (l8 == 0) { sh.t[cur] = hit_t; sh.u[cur] = hit_u; sh.v[cur] = hit_v; sh.slot[cur] = hit_slot; }
+              cur = -1;
+              continue;
+            }
+            const int up = __ffs(pending) - 1;
+            pending &= pending - 1;
+            for (; level < up; level++) node = (node - 1) >> 3;
+            entry = my_levels[level * 8];
             continue;
           }
-          node = (node - 1) >> 3;                        // back to the parent
-          level += 1;
-          entry = my_levels[level * 8];
-          continue;
+          const unsigned below = (__ballot_sync(omask, key < hit_bits) >> (lane & 24)) & 0xffu;
+          const unsigned who   = (__ballot_sync(omask, key == best) >> (lane & 24)) & 0xffu;
+          const int pick = __ffs(who) - 1;                 // lowest index on ties
+          if (l8 == pick) entry = CUDART_INF_F;            // raytracer.c:481
+          const int child = 8 * node + 1 + pick;
+          if (level == 1) {
+            leaf = child - sc.n_internal;
+          } else {
+            if (below & (below - 1)) {                     // more than one candidate: remember this level
+              my_levels[level * 8] = entry;
+              pending |= 1u << level;
+            }
+            node = child;
+            level -= 1;
+            need_box = true;
+          }
+#if !RT_BATCH_LEAF
+          break;
+#endif
         }
-        unsigned who = (__ballot_sync(omask, key == best) >> (lane & 24)) & 0xffu;
-        int pick = __ffs(who) - 1;                       // lowest index on ties
-        if (l8 == pick) entry = CUDART_INF_F;            // raytracer.c:481
-        int child = 8 * node + 1 + pick;
+        if (finished) break;
+        if (leaf < 0) continue;
 
-        if (level == 1) {
-          // -------- raytracer.c:84-188: eight Möller–Trumbore tests, one per lane
-          int leaf = child - sc.n_internal;
+        // ---- raytracer.c:84-188: eight Möller–Trumbore tests, one per lane.
+        // leaf rows hold p0 and the edges e1 = p1 - p0, e2 = p2 - p0 (the same f32
+        // subtractions raytracer.c:116-122 does per ray, done once at upload)
+        {
           const float *lp = sc.leaf_pos + (size_t)leaf * 72 + l8;
-          float p0x = __ldg(lp +  0), p1x = __ldg(lp +  8), p2x = __ldg(lp + 16);
-          float p0y = __ldg(lp + 24), p1y = __ldg(lp + 32), p2y = __ldg(lp + 40);
-          float p0z = __ldg(lp + 48), p1z = __ldg(lp + 56), p2z = __ldg(lp + 64);
+          float p0x = __ldg(lp +  0), p0y = __ldg(lp +  8), p0z = __ldg(lp + 16);
+          float e1x = __ldg(lp + 24), e1y = __ldg(lp + 32), e1z = __ldg(lp + 40);
+          float e2x = __ldg(lp + 48), e2y = __ldg(lp + 56), e2z = __ldg(lp + 64);
           c_leaves++;
-          float e1x = p1x - p0x, e1y = p1y - p0y, e1z = p1z - p0z;
-          float e2x = p2x - p0x, e2y = p2y - p0y, e2z = p2z - p0z;
           float pvx = dy * e2z - dz * e2y, pvy = dz * e2x - dx * e2z, pvz = dx * e2y - dy * e2x;
           float det = e1x * pvx + e1y * pvy + e1z * pvz;
           float inv_det = 1.0f / det;
@@ -227,12 +295,7 @@ rt_render_kernel(const __grid_constant__ RenderParams P) {
             hit_v = __shfl_sync(omask, v, w);
             c_accepts++;
           }
-        } else {
-          my_levels[level * 8] = entry;                  // remember this level's distances
-          node = child;
-          level -= 1;
-          entry = child_entry(sc.nodes + (size_t)node * 48 + l8, ox, oy, oz, ix, iy, iz, hit_t);
-          c_nodes++;
+          leaf = -1;
         }
       }
     }
@@ -240,8 +303,7 @@ rt_render_kernel(const __grid_constant__ RenderParams P) {
 
     // --------------------------------------------------------------------- shade
     if (has_path) {
-      const Mailbox &m = mail[tid];
-      const int slot = m.slot;
+      const int slot = sh.slot[tid];
       bool done = false;
       V3 radiance = mk3(0, 0, 0);
 
@@ -250,16 +312,15 @@ rt_render_kernel(const __grid_constant__ RenderParams P) {
       if (slot < 0) {
         // raytracer.c:554
         c_misses++;
-        radiance = add3(mul3(environment(sc, d), tint), emis);
+        radiance = add3(mul3(environment(sc, sh.texel_lut, d), tint), emis);
         done = true;
       } else {
         const float4 *rec = sc.tri_rec + (size_t)slot * 7;
-        float4 r0 = __ldg(rec + 0), r1 = __ldg(rec + 1), r2 = __ldg(rec + 2), r3 = __ldg(rec + 3);
-        float4 r4 = __ldg(rec + 4), r5 = __ldg(rec + 5), r6 = __ldg(rec + 6);
+        float4 r0 = __ldg(rec + 0), r1 = __ldg(rec + 1), r2 = __ldg(rec + 2);
         V3 ng = mk3(r0.x, r0.y, r0.z);
         V3 na = mk3(r0.w, r1.x, r1.y), nb = mk3(r1.z, r1.w, r2.x), nc = mk3(r2.y, r2.z, r2.w);
-        float w1 = m.u, w2 = m.v, w0 = 1 - w1 - w2;           // raytracer.c:164-177
-        V3 point  = add3(o, scale3(d, m.t));
+        float w1 = sh.u[tid], w2 = sh.v[tid], w0 = 1 - w1 - w2;           // raytracer.c:164-177
+        V3 point  = add3(o, scale3(d, sh.t[tid]));
         V3 normal = mk3(na.x * w0 + nb.x * w1 + nc.x * w2,
                         na.y * w0 + nb.y * w1 + nc.y * w2,
                         na.z * w0 + nb.z * w1 + nc.z * w2);
@@ -268,6 +329,7 @@ rt_render_kernel(const __grid_constant__ RenderParams P) {
           c_pass++;
           o = add3(point, scale3(d, RT_EPS));
         } else {
+          float4 r3 = __ldg(rec + 3), r4 = __ldg(rec + 4), r5 = __ldg(rec + 5), r6 = __ldg(rec + 6);
           ShadeIn in;
           in.dir = d;
           in.normal = normalize3(normal);
@@ -278,7 +340,7 @@ rt_render_kernel(const __grid_constant__ RenderParams P) {
           in.v = r4.w * w0 + r5.y * w1 + r5.w * w2;
           ShadeOut out;
           c_shades++;
-          shade_pbr(sc, __float_as_int(r6.x), in, rng, out);
+          shade_pbr(sc, sh.texel_lut, __float_as_int(r6.x), in, rng, out);
           emis = add3(emis, mul3(out.emission, tint));          // raytracer.c:537
           if (out.terminate) {
             radiance = emis;

@@ -19,13 +19,14 @@ struct ShadeOut { V3 dir, tint, emission; bool terminate; };
 
 __device__ __forceinline__ float rnd(uint32_t &state) { return rt_rand_f32(&state); }
 
-__device__ __forceinline__ V3 texel_rgb(const TextureDev &tex, int x, int y) {
+// lut[i] = (float)i / 255.999f, built once per block with the same IEEE division (driver.c:69-88)
+__device__ __forceinline__ V3 texel_rgb(const TextureDev &tex, const float *lut, int x, int y) {
   uchar4 t = __ldg(&tex.texels[x + tex.width * y]);
-  return mk3((float)t.x / 255.999f, (float)t.y / 255.999f, (float)t.z / 255.999f);
+  return mk3(lut[t.x], lut[t.y], lut[t.z]);
 }
 
 // driver.c:49-93: negative wrap, fract, no half-texel offset, +1 neighbour clamped
-__device__ __noinline__ V3 sample_bilinear(const TextureDev &tex, float u, float v) {
+__device__ __noinline__ V3 sample_bilinear(const TextureDev &tex, const float *lut, float u, float v) {
   if (u < 0) u += (float)(-(int)u + 1);
   if (v < 0) v += (float)(-(int)v + 1);
   u = u - floorf(u);
@@ -36,8 +37,8 @@ __device__ __noinline__ V3 sample_bilinear(const TextureDev &tex, float u, float
   float a = px - (float)x0, b = py - (float)y0;
   int x1 = (x0 + 1 < tex.width)  ? x0 + 1 : x0;
   int y1 = (y0 + 1 < tex.height) ? y0 + 1 : y0;
-  V3 top = lerp3(texel_rgb(tex, x0, y0), texel_rgb(tex, x1, y0), a);
-  V3 bot = lerp3(texel_rgb(tex, x0, y1), texel_rgb(tex, x1, y1), a);
+  V3 top = lerp3(texel_rgb(tex, lut, x0, y0), texel_rgb(tex, lut, x1, y0), a);
+  V3 bot = lerp3(texel_rgb(tex, lut, x0, y1), texel_rgb(tex, lut, x1, y1), a);
   return lerp3(top, bot, b);
 }
 
@@ -49,12 +50,12 @@ __device__ __forceinline__ V3 decode_srgb(V3 c) {
 }
 
 // driver.c:95-104 (asin argument clamped: DESIGN.md deviation list)
-__device__ __noinline__ V3 environment(const SceneDev &sc, V3 dir) {
+__device__ __noinline__ V3 environment(const SceneDev &sc, const float *lut, V3 dir) {
   float inv_pi     = (float)(1.0f / RT_PI);
   float inv_two_pi = (float)(1.0f / (2.0f * RT_PI));
   float u = 0.5f + rt_atan2f(dir.z, dir.x) * inv_two_pi;
   float v = 0.5f - rt_asinf(clamp1(dir.y, -1.0f, 1.0f)) * inv_pi;
-  return decode_srgb(sample_bilinear(sc.textures[sc.env_texture], u, v));
+  return decode_srgb(sample_bilinear(sc.textures[sc.env_texture], lut, u, v));
 }
 
 __device__ __forceinline__ float luma(V3 c) { return dot3(c, mk3(0.2126f, 0.7152f, 0.0722f)); }
@@ -117,13 +118,13 @@ __device__ __forceinline__ V3 sheen_term(float sheen, V3 base, float sheen_tint,
 }
 
 // driver.c:350-409 with :287-348 inlined
-__device__ __noinline__ void shade_pbr(const SceneDev &sc, int material, const ShadeIn &in, uint32_t &rng, ShadeOut &out) {
+__device__ __noinline__ void shade_pbr(const SceneDev &sc, const float *lut, int material, const ShadeIn &in, uint32_t &rng, ShadeOut &out) {
   const MaterialDev &mat = sc.materials[material];
 
   // driver.c:129-153
   V3 n = in.normal;
   if (mat.tex_normal >= 0) {
-    V3 s = sample_bilinear(sc.textures[mat.tex_normal], in.u, in.v);
+    V3 s = sample_bilinear(sc.textures[mat.tex_normal], lut, in.u, in.v);
     s = add3(scale3(s, 2.0f), mk3(-1, -1, -1));
     s.y *= -1;
     V3 t = in.tangent, b = in.bitangent;
@@ -134,11 +135,11 @@ __device__ __noinline__ void shade_pbr(const SceneDev &sc, int material, const S
   }
 
   V3 base = mk3(mat.base[0], mat.base[1], mat.base[2]);
-  if (mat.tex_albedo >= 0) base = mul3(base, decode_srgb(sample_bilinear(sc.textures[mat.tex_albedo], in.u, in.v)));
+  if (mat.tex_albedo >= 0) base = mul3(base, decode_srgb(sample_bilinear(sc.textures[mat.tex_albedo], lut, in.u, in.v)));
 
   float roughness = mat.roughness, metalness = mat.metalness;
   if (mat.tex_mr >= 0) {
-    V3 mr = sample_bilinear(sc.textures[mat.tex_mr], in.u, in.v);
+    V3 mr = sample_bilinear(sc.textures[mat.tex_mr], lut, in.u, in.v);
     roughness *= mr.y;
     metalness *= mr.z;
   }
@@ -147,7 +148,7 @@ __device__ __noinline__ void shade_pbr(const SceneDev &sc, int material, const S
   metalness /= 0.9f;
 
   V3 glow = mk3(mat.emission[0], mat.emission[1], mat.emission[2]);
-  if (mat.tex_emission >= 0) glow = mul3(glow, decode_srgb(sample_bilinear(sc.textures[mat.tex_emission], in.u, in.v)));
+  if (mat.tex_emission >= 0) glow = mul3(glow, decode_srgb(sample_bilinear(sc.textures[mat.tex_emission], lut, in.u, in.v)));
   out.emission = glow;
   out.terminate = false;
   out.tint = mk3(0, 0, 0);
