@@ -8,24 +8,21 @@
 //   * Every lane owns one PATH and one PIXEL JOB.  A job is "all samples
 //     [sample_begin, sample_end) of one pixel", pulled from a global atomic
 //     counter in 8x4-pixel tile order (the GPU form of the reference's atomic
-//     32x32 chunk queue, raytracer.c:619-627).  The lane sums its samples in
-//     sample order in registers and writes the pixel once, so the f32 sum is
-//     bit-identical to the sequential CPU loop.  When a path ends the lane starts
-//     the next sample (or pulls the next pixel) — lanes never idle on finished paths.
-//   * TRAVERSAL is cooperative: the reference's AVX2 design tests 8 child boxes /
-//     8 triangles per instruction; here an OCTET (8 adjacent lanes) does the same,
-//     one child box or one triangle per lane, with __shfl_xor min-reductions in
-//     place of the horizontal min.  The warp's (up to) 32 rays sit in a shared-
-//     memory mailbox; each of the 4 octets pulls the next ray from a per-warp
-//     bitmask when it finishes one, so octets stay busy until the mailbox drains.
-//     The walk is a flat state machine (no recursion, no stack): the tree is a
-//     complete 8-ary heap, parent = (n-1)>>3; per-level entry distances live in
-//     shared memory and a bitmask of levels that still hold untried children lets
-//     a pop jump straight to the next useful ancestor.  Box tests / selection run
-//     in one uniform loop body; leaf tests are batched behind it so octets of a
-//     warp execute the long Möller–Trumbore body together instead of serialising
-//     it against box tests.  Node rows are 32-byte sectors, so an octet's 6 loads
-//     per box test and 9 per leaf are fully coalesced.
+//     32x32 chunk queue, raytracer.c:619-627), so the 32 lanes of a warp always
+//     work on one 8x4 tile and their primary rays stay coherent.  The lane sums
+//     its samples in sample order in registers and writes the pixel once, so the
+//     f32 sum is bit-identical to the sequential CPU loop.  When a path ends the
+//     lane starts the next sample (or pulls the next pixel) — lanes never idle
+//     on finished paths.
+//   * TRAVERSAL is one thread per ray (trace_ray): the reference's AVX2 8-wide box
+//     and triangle tests become eight unrolled scalar tests per lane, so a warp
+//     tests 256 boxes per node step with no cross-lane traffic.  The walk is a flat
+//     while-while loop (no recursion): internal nodes until a leaf is found, then
+//     the warp runs the Möller–Trumbore body together.  Entry distances of levels
+//     with untried children are parked in shared memory ([level][2][thread]
+//     float4, conflict-free), a bitmask of such levels lets a pop jump straight
+//     to the next useful ancestor.  Node and leaf rows are read as 16-byte
+//     vectors (12 per node, 18 per leaf), warp-uniform for coherent rays.
 //   * SHADING is per lane (rt_shade.cuh), all 32 lanes of the warp active.
 // Arithmetic is IEEE f32 without FMA contraction (-fmad=false) in the reference's
 // operation order: primary-hit slots and radiance equal the CPU oracle bit for bit.
@@ -39,9 +36,6 @@
 #define RT_BLOCK 256
 #ifndef RT_MIN_BLOCKS
 #define RT_MIN_BLOCKS 3
-#endif
-#ifndef RT_BATCH_LEAF
-#define RT_BATCH_LEAF 1
 #endif
 
 // raytracer.c:582-594, one lane of hash12x8
@@ -61,16 +55,17 @@ __device__ __forceinline__ float hash12(float px, float py) {
 // rule never fires and the hardware FMNMX gives the same value (a zero's sign can
 // differ, but `enter` is >= EPS and `leave` is only compared).  Otherwise the exact
 // operand-order selects are used (0 * inf lanes, raytracer.c:212-225).
-__device__ __forceinline__ float child_entry(const float *__restrict__ row, float ox, float oy, float oz,
-                                             float ix, float iy, float iz, float t_max, bool regular) {
-  float ax = (__ldg(row +  0) - ox) * ix;
-  float ay = (__ldg(row +  8) - oy) * iy;
-  float az = (__ldg(row + 16) - oz) * iz;
-  float bx = (__ldg(row + 24) - ox) * ix;
-  float by = (__ldg(row + 32) - oy) * iy;
-  float bz = (__ldg(row + 40) - oz) * iz;
+template <bool REGULAR>
+__device__ __forceinline__ float child_entry(float lox, float loy, float loz, float hix, float hiy, float hiz,
+                                             float ox, float oy, float oz, float ix, float iy, float iz, float t_max) {
+  float ax = (lox - ox) * ix;
+  float ay = (loy - oy) * iy;
+  float az = (loz - oz) * iz;
+  float bx = (hix - ox) * ix;
+  float by = (hiy - oy) * iy;
+  float bz = (hiz - oz) * iz;
   float enter, leave;
-  if (regular) {
+  if (REGULAR) {
     enter = fmaxf(RT_EPS, fmaxf(fminf(ax, bx), fmaxf(fminf(ay, by), fminf(az, bz))));
     leave = fminf(t_max,  fminf(fmaxf(ax, bx), fminf(fmaxf(ay, by), fmaxf(az, bz))));
   } else {
@@ -82,34 +77,143 @@ __device__ __forceinline__ float child_entry(const float *__restrict__ row, floa
   return (enter >= leave) ? CUDART_INF_F : enter;
 }
 
-__device__ __forceinline__ unsigned octet_min(unsigned omask, unsigned key) {
-  key = min(key, __shfl_xor_sync(omask, key, 1));
-  key = min(key, __shfl_xor_sync(omask, key, 2));
-  key = min(key, __shfl_xor_sync(omask, key, 4));
-  return key;
+// raytracer.c:190-230, ray_aabbs_hit_8: the eight children of one node, entry distance or +inf.
+// A node is six 32-byte rows (min x/y/z, max x/y/z; child j in column j): twelve 16-byte loads,
+// warp-uniform for coherent rays.
+template <bool REGULAR>
+__device__ __forceinline__ void node_entries(const float4 *__restrict__ n4, float ox, float oy, float oz,
+                                             float ix, float iy, float iz, float t_max, float (&e)[8]) {
+  #pragma unroll
+  for (int h = 0; h < 2; h++) {
+    float4 lx = __ldg(n4 + 0 + h), ly = __ldg(n4 + 2 + h), lz = __ldg(n4 + 4 + h);
+    float4 hx = __ldg(n4 + 6 + h), hy = __ldg(n4 + 8 + h), hz = __ldg(n4 + 10 + h);
+    e[4 * h + 0] = child_entry<REGULAR>(lx.x, ly.x, lz.x, hx.x, hy.x, hz.x, ox, oy, oz, ix, iy, iz, t_max);
+    e[4 * h + 1] = child_entry<REGULAR>(lx.y, ly.y, lz.y, hx.y, hy.y, hz.y, ox, oy, oz, ix, iy, iz, t_max);
+    e[4 * h + 2] = child_entry<REGULAR>(lx.z, ly.z, lz.z, hx.z, hy.z, hz.z, ox, oy, oz, ix, iy, iz, t_max);
+    e[4 * h + 3] = child_entry<REGULAR>(lx.w, ly.w, lz.w, hx.w, hy.w, hz.w, ox, oy, oz, ix, iy, iz, t_max);
+  }
+}
+
+// fminf ignores NaN operands: the minimum of the ordered entries (NaN only if all eight are NaN)
+__device__ __forceinline__ float min8(const float (&e)[8]) {
+  return fminf(fminf(fminf(e[0], e[1]), fminf(e[2], e[3])), fminf(fminf(e[4], e[5]), fminf(e[6], e[7])));
+}
+
+// raytracer.c:84-188 for ONE triangle of a leaf; p0 and the edges e1 = p1 - p0, e2 = p2 - p0
+// (the same f32 subtractions raytracer.c:116-122 does per ray, done once at upload).
+// Strict <, ascending j: the lowest lane wins a tie inside the leaf and an earlier leaf wins
+// across leaves (raytracer.c:15-32 with eps 0, :159).
+__device__ __forceinline__ void triangle_test(float p0x, float p0y, float p0z, float e1x, float e1y, float e1z,
+                                              float e2x, float e2y, float e2z, float ox, float oy, float oz,
+                                              float dx, float dy, float dz, int slot,
+                                              float &hit_t, float &hit_u, float &hit_v, int &hit_slot) {
+  float pvx = dy * e2z - dz * e2y, pvy = dz * e2x - dx * e2z, pvz = dx * e2y - dy * e2x;
+  float det = e1x * pvx + e1y * pvy + e1z * pvz;
+  float inv_det = 1.0f / det;
+  float tvx = ox - p0x, tvy = oy - p0y, tvz = oz - p0z;
+  float qvx = tvy * e1z - tvz * e1y, qvy = tvz * e1x - tvx * e1z, qvz = tvx * e1y - tvy * e1x;
+  float u = inv_det * (tvx * pvx + tvy * pvy + tvz * pvz);
+  float v = inv_det * (dx * qvx + dy * qvy + dz * qvz);
+  float t = inv_det * (e2x * qvx + e2y * qvy + e2z * qvz);
+  bool miss = (u < -RT_EPS) | (u > 1 + RT_EPS) | (v < -RT_EPS) | (u + v > 1 + RT_EPS) | (t < RT_EPS);
+  // t <= 0 and NaN count as +inf (min_f32x8 with eps 0); NaN also fails the ordered compare
+  if (!miss && t > 0.0f && t < hit_t) { hit_t = t; hit_u = u; hit_v = v; hit_slot = slot; }
+}
+
+// per-thread slice of the level store: levels[(level - 1) * 2 + half][tid]
+#define RT_LEVELS(level, half) levels[(((level) - 1) * 2 + (half)) * RT_BLOCK]
+
+// raytracer.c:443-503: closest hit of one ray, one thread per ray.
+// The reference recursion (8 entry distances per level on the C stack, up to 8 selection
+// rounds per node) is a flat loop here: the tree is a complete 8-ary heap, parent = (n-1)>>3;
+// the current node's entry distances live in registers, those of ancestors that still hold
+// untried candidates in shared memory, and `pending` (bit = level) lets a pop jump straight
+// to the nearest such ancestor.  Visit order and every compare are the reference's, so the
+// closest hit — ties included — is the same triangle slot.
+template <bool REGULAR>
+__device__ __forceinline__ void trace_ray(const SceneDev &sc, float4 *levels, float ox, float oy, float oz,
+                                          float dx, float dy, float dz, float ix, float iy, float iz,
+                                          float &hit_t, float &hit_u, float &hit_v,
+                                          int &hit_slot, unsigned &c_nodes, unsigned &c_leaves, unsigned &c_accepts) {
+  int      node = 0, level = sc.depth;                                 // raytracer.c:501
+  unsigned pending = 0;
+  bool     need_box = true;
+  float    e[8];
+  hit_t = CUDART_INF_F; hit_u = 0; hit_v = 0; hit_slot = -1;
+
+  for (;;) {
+    int leaf = -1;
+    // ---- walk internal nodes until this ray holds a leaf to test (or is finished); lanes
+    // that found one wait here so the warp runs the long triangle body together
+    for (;;) {
+      if (need_box) {
+        node_entries<REGULAR>((const float4 *)(sc.nodes + (size_t)node * 48), ox, oy, oz, ix, iy, iz, hit_t, e);
+        need_box = false;
+        c_nodes++;
+      }
+      // raytracer.c:459-472: nearest untried child strictly below the current hit, lowest index on ties
+      const float best = min8(e);
+      if (!(best < hit_t)) {
+        if (pending == 0) break;
+        const int up = __ffs(pending) - 1;
+        pending &= pending - 1;
+        for (; level < up; level++) node = (node - 1) >> 3;
+        float4 a = RT_LEVELS(level, 0), b = RT_LEVELS(level, 1);
+        e[0] = a.x; e[1] = a.y; e[2] = a.z; e[3] = a.w; e[4] = b.x; e[5] = b.y; e[6] = b.z; e[7] = b.w;
+        continue;
+      }
+      int pick = 7;
+      #pragma unroll
+      for (int j = 6; j >= 0; j--) pick = (e[j] == best) ? j : pick;
+      #pragma unroll
+      for (int j = 0; j < 8; j++) e[j] = (j == pick) ? CUDART_INF_F : e[j];       // raytracer.c:481
+      const int child = 8 * node + 1 + pick;
+      if (level == 1) { leaf = child - sc.n_internal; break; }
+      if (min8(e) < hit_t) {                         // other candidates remain: remember this level
+        RT_LEVELS(level, 0) = make_float4(e[0], e[1], e[2], e[3]);
+        RT_LEVELS(level, 1) = make_float4(e[4], e[5], e[6], e[7]);
+        pending |= 1u << level;
+      }
+      node = child;
+      level -= 1;
+      need_box = true;
+    }
+    if (leaf < 0) return;
+
+    // ---- raytracer.c:84-188: the eight triangles of the leaf (nine 32-byte rows)
+    {
+      const float4 *lp = (const float4 *)(sc.leaf_pos + (size_t)leaf * 72);
+      c_leaves++;
+      const float t_before = hit_t;
+      #pragma unroll
+      for (int h = 0; h < 2; h++) {
+        float4 p0x = __ldg(lp +  0 + h), p0y = __ldg(lp +  2 + h), p0z = __ldg(lp +  4 + h);
+        float4 e1x = __ldg(lp +  6 + h), e1y = __ldg(lp +  8 + h), e1z = __ldg(lp + 10 + h);
+        float4 e2x = __ldg(lp + 12 + h), e2y = __ldg(lp + 14 + h), e2z = __ldg(lp + 16 + h);
+        const int s0 = leaf * 8 + 4 * h;
+        triangle_test(p0x.x, p0y.x, p0z.x, e1x.x, e1y.x, e1z.x, e2x.x, e2y.x, e2z.x, ox, oy, oz, dx, dy, dz, s0 + 0, hit_t, hit_u, hit_v, hit_slot);
+        triangle_test(p0x.y, p0y.y, p0z.y, e1x.y, e1y.y, e1z.y, e2x.y, e2y.y, e2z.y, ox, oy, oz, dx, dy, dz, s0 + 1, hit_t, hit_u, hit_v, hit_slot);
+        triangle_test(p0x.z, p0y.z, p0z.z, e1x.z, e1y.z, e1z.z, e2x.z, e2y.z, e2z.z, ox, oy, oz, dx, dy, dz, s0 + 2, hit_t, hit_u, hit_v, hit_slot);
+        triangle_test(p0x.w, p0y.w, p0z.w, e1x.w, e1y.w, e1z.w, e2x.w, e2y.w, e2z.w, ox, oy, oz, dx, dy, dz, s0 + 3, hit_t, hit_u, hit_v, hit_slot);
+      }
+      if (hit_t < t_before) c_accepts++;
+    }
+  }
 }
 
 struct Shared {
-  float ox[RT_BLOCK], oy[RT_BLOCK], oz[RT_BLOCK], dx[RT_BLOCK], dy[RT_BLOCK], dz[RT_BLOCK];   // in:  rays
-  float t[RT_BLOCK], u[RT_BLOCK], v[RT_BLOCK];                                                 // out: closest hits
-  int   slot[RT_BLOCK];
-  float level_entry[RT_BLOCK / 8][RT_MAX_DEPTH + 1][8];
   float texel_lut[256];
-  unsigned todo[RT_BLOCK / 32];
 };
 
 __global__ void __launch_bounds__(RT_BLOCK, RT_MIN_BLOCKS)
 rt_render_kernel(const __grid_constant__ RenderParams P) {
   __shared__ Shared sh;
+  extern __shared__ float4 level_store[];          // [depth][2][RT_BLOCK] entry distances of pending levels
 
   const SceneDev &sc = P.scene;
   const int tid   = threadIdx.x;
   const int lane  = tid & 31;
-  const int l8    = tid & 7;
-  const int wbase = tid & ~31;
-  const unsigned omask = 0xffu << (lane & 24);
-  float *my_levels = &sh.level_entry[tid >> 3][0][l8];
-  volatile unsigned *todo = &sh.todo[tid >> 5];
+  float4 *levels = level_store + tid;
 
   // u8 -> f32 texel table: the same IEEE division the reference does per tap
   // (driver.c:69-88), done once per block instead of 12 times per bilinear fetch
@@ -133,7 +237,6 @@ rt_render_kernel(const __grid_constant__ RenderParams P) {
   V3   o = eye, d = mk3(0, 0, -1), tint = mk3(1, 1, 1), emis = mk3(0, 0, 0);
   int  bounce = 0;
   uint32_t rng = 0;
-  // counters (octet leader counts traversal work, every lane counts its paths)
   unsigned c_rays = 0, c_nodes = 0, c_leaves = 0, c_accepts = 0, c_shades = 0, c_misses = 0, c_pass = 0, c_samples = 0;
 
   for (;;) {
@@ -175,135 +278,24 @@ rt_render_kernel(const __grid_constant__ RenderParams P) {
         has_path = true;
       }
     }
-    const unsigned active = __ballot_sync(0xffffffffu, has_path);
-    if (active == 0) break;
+    if (__ballot_sync(0xffffffffu, has_path) == 0) break;
 
     // --------------------------------------------------------------------- trace
+    float hit_t = CUDART_INF_F, hit_u = 0, hit_v = 0;
+    int   slot = -1;
     if (has_path) {
-      sh.ox[tid] = o.x; sh.oy[tid] = o.y; sh.oz[tid] = o.z;
-      sh.dx[tid] = d.x; sh.dy[tid] = d.y; sh.dz[tid] = d.z;
       c_rays++;
-    }
-    if (lane == 0) *todo = active;
-    __syncwarp();
-    {
-      int   cur = -1, node = 0, level = 0, hit_slot = -1, leaf = -1;
-      unsigned pending = 0;               // levels (bit = level) that still hold untried children
-      bool  need_box = false, regular = true, finished = false;
-      float ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 0, ix = 0, iy = 0, iz = 0;
-      float hit_t = CUDART_INF_F, hit_u = 0, hit_v = 0, entry = CUDART_INF_F;
-
-      for (;;) {
-        // ---- uniform part: fetch / box test / select / pop, until this octet holds a leaf to test
-        while (!finished && leaf < 0) {
-          if (cur < 0) {
-            int got = -1;
-            if (l8 == 0) {                               // the octet leader claims the next ray of the warp
-              unsigned seen = *todo;
-              while (seen) {
-                unsigned bit = seen & (0u - seen);
-                unsigned prev = atomicCAS((unsigned *)todo, seen, seen ^ bit);
-                if (prev == seen) { got = __ffs(bit) - 1; break; }
-                seen = prev;
-              }
-            }
-            got = __shfl_sync(omask, got, lane & 24);
-            if (got < 0) { finished = true; break; }
-            cur = wbase + got;
-            ox = sh.ox[cur]; oy = sh.oy[cur]; oz = sh.oz[cur];
-            dx = sh.dx[cur]; dy = sh.dy[cur]; dz = sh.dz[cur];
-            ix = 1.0f / dx; iy = 1.0f / dy; iz = 1.0f / dz;         // raytracer.c:198-202
-            regular = (fabsf(ix) < CUDART_INF_F) & (fabsf(iy) < CUDART_INF_F) & (fabsf(iz) < CUDART_INF_F);
-            hit_t = CUDART_INF_F; hit_slot = -1; hit_u = 0; hit_v = 0;
-            node = 0; level = sc.depth; pending = 0;                   // raytracer.c:501
-            need_box = true;
-          }
-          if (need_box) {
-            entry = child_entry(sc.nodes + (size_t)node * 48 + l8, ox, oy, oz, ix, iy, iz, hit_t, regular);
-            need_box = false;
-            c_nodes++;
-          }
-          // raytracer.c:459-472: nearest unvisited child strictly below the current hit.
-          // entry is >= EPS, +inf or NaN: its u32 order equals its f32 order
-          const unsigned hit_bits = __float_as_uint(hit_t);
-          const unsigned key  = __float_as_uint(entry);
-          const unsigned best = octet_min(omask, key);
-          if (best >= hit_bits) {
-            // nothing left under this node: jump to the nearest ancestor with untried children
-            if (pending == 0) {
-              if (l8 == 0) { sh.t[cur] = hit_t; sh.u[cur] = hit_u; sh.v[cur] = hit_v; sh.slot[cur] = hit_slot; }
-              cur = -1;
-              continue;
-            }
-            const int up = __ffs(pending) - 1;
-            pending &= pending - 1;
-            for (; level < up; level++) node = (node - 1) >> 3;
-            entry = my_levels[level * 8];
-            continue;
-          }
-          const unsigned below = (__ballot_sync(omask, key < hit_bits) >> (lane & 24)) & 0xffu;
-          const unsigned who   = (__ballot_sync(omask, key == best) >> (lane & 24)) & 0xffu;
-          const int pick = __ffs(who) - 1;                 // lowest index on ties
-          if (l8 == pick) entry = CUDART_INF_F;            // raytracer.c:481
-          const int child = 8 * node + 1 + pick;
-          if (level == 1) {
-            leaf = child - sc.n_internal;
-          } else {
-            if (below & (below - 1)) {                     // more than one candidate: remember this level
-              my_levels[level * 8] = entry;
-              pending |= 1u << level;
-            }
-            node = child;
-            level -= 1;
-            need_box = true;
-          }
-#if !RT_BATCH_LEAF
-          break;
-#endif
-        }
-        if (finished) break;
-        if (leaf < 0) continue;
-
-        // ---- raytracer.c:84-188: eight Möller–Trumbore tests, one per lane.
-        // leaf rows hold p0 and the edges e1 = p1 - p0, e2 = p2 - p0 (the same f32
-        // subtractions raytracer.c:116-122 does per ray, done once at upload)
-        {
-          const float *lp = sc.leaf_pos + (size_t)leaf * 72 + l8;
-          float p0x = __ldg(lp +  0), p0y = __ldg(lp +  8), p0z = __ldg(lp + 16);
-          float e1x = __ldg(lp + 24), e1y = __ldg(lp + 32), e1z = __ldg(lp + 40);
-          float e2x = __ldg(lp + 48), e2y = __ldg(lp + 56), e2z = __ldg(lp + 64);
-          c_leaves++;
-          float pvx = dy * e2z - dz * e2y, pvy = dz * e2x - dx * e2z, pvz = dx * e2y - dy * e2x;
-          float det = e1x * pvx + e1y * pvy + e1z * pvz;
-          float inv_det = 1.0f / det;
-          float tvx = ox - p0x, tvy = oy - p0y, tvz = oz - p0z;
-          float qvx = tvy * e1z - tvz * e1y, qvy = tvz * e1x - tvx * e1z, qvz = tvx * e1y - tvy * e1x;
-          float u = inv_det * (tvx * pvx + tvy * pvy + tvz * pvz);
-          float v = inv_det * (dx * qvx + dy * qvy + dz * qvz);
-          float t = inv_det * (e2x * qvx + e2y * qvy + e2z * qvz);
-          bool miss = (u < -RT_EPS) | (u > 1 + RT_EPS) | (v < -RT_EPS) | (u + v > 1 + RT_EPS) | (t < RT_EPS);
-          // raytracer.c:15-32 with eps 0: lanes <= 0 or NaN count as +inf
-          float cand = (!miss && t > 0.0f) ? t : CUDART_INF_F;
-          unsigned ck = __float_as_uint(cand);
-          unsigned cbest = octet_min(omask, ck);
-          if (cbest < __float_as_uint(hit_t)) {          // strict <, raytracer.c:159
-            unsigned cw = (__ballot_sync(omask, ck == cbest) >> (lane & 24)) & 0xffu;
-            int w = (lane & 24) + __ffs(cw) - 1;
-            hit_t = __uint_as_float(cbest);
-            hit_slot = leaf * 8 + (w & 7);
-            hit_u = __shfl_sync(omask, u, w);
-            hit_v = __shfl_sync(omask, v, w);
-            c_accepts++;
-          }
-          leaf = -1;
-        }
-      }
+      // a zero direction component makes 1/d infinite and 0 * inf NaN: only then the slab test
+      // needs the exact MINPS/MAXPS operand-order rule (see child_entry)
+      const float ix = 1.0f / d.x, iy = 1.0f / d.y, iz = 1.0f / d.z;         // raytracer.c:198-202
+      const bool regular = (fabsf(ix) < CUDART_INF_F) & (fabsf(iy) < CUDART_INF_F) & (fabsf(iz) < CUDART_INF_F);
+      if (regular) trace_ray<true >(sc, levels, o.x, o.y, o.z, d.x, d.y, d.z, ix, iy, iz, hit_t, hit_u, hit_v, slot, c_nodes, c_leaves, c_accepts);
+      else         trace_ray<false>(sc, levels, o.x, o.y, o.z, d.x, d.y, d.z, ix, iy, iz, hit_t, hit_u, hit_v, slot, c_nodes, c_leaves, c_accepts);
     }
     __syncwarp();
 
     // --------------------------------------------------------------------- shade
     if (has_path) {
-      const int slot = sh.slot[tid];
       bool done = false;
       V3 radiance = mk3(0, 0, 0);
 
@@ -319,8 +311,8 @@ rt_render_kernel(const __grid_constant__ RenderParams P) {
         float4 r0 = __ldg(rec + 0), r1 = __ldg(rec + 1), r2 = __ldg(rec + 2);
         V3 ng = mk3(r0.x, r0.y, r0.z);
         V3 na = mk3(r0.w, r1.x, r1.y), nb = mk3(r1.z, r1.w, r2.x), nc = mk3(r2.y, r2.z, r2.w);
-        float w1 = sh.u[tid], w2 = sh.v[tid], w0 = 1 - w1 - w2;           // raytracer.c:164-177
-        V3 point  = add3(o, scale3(d, sh.t[tid]));
+        float w1 = hit_u, w2 = hit_v, w0 = 1 - w1 - w2;           // raytracer.c:164-177
+        V3 point  = add3(o, scale3(d, hit_t));
         V3 normal = mk3(na.x * w0 + nb.x * w1 + nc.x * w2,
                         na.y * w0 + nb.y * w1 + nc.y * w2,
                         na.z * w0 + nb.z * w1 + nc.z * w2);
@@ -374,7 +366,6 @@ rt_render_kernel(const __grid_constant__ RenderParams P) {
     #pragma unroll
     for (int k = 0; k < 8; k++) {
       unsigned v = vals[k];
-      if ((k >= 1 && k <= 3) && l8 != 0) v = 0;           // traversal work is per octet
       v += __shfl_xor_sync(0xffffffffu, v, 16);
       v += __shfl_xor_sync(0xffffffffu, v, 8);
       v += __shfl_xor_sync(0xffffffffu, v, 4);
@@ -406,12 +397,17 @@ __global__ void rt_resolve_kernel(const float *__restrict__ accum, int width, in
 
 // ------------------------------------------------------------------- launchers
 static int g_blocks_per_sm = 0;
+static size_t g_level_bytes = 0;
 
 int rt_launch_render(const RenderParams &p, int sm_count, cudaStream_t stream) {
-  if (g_blocks_per_sm == 0) {
+  // level store: [depth][2][RT_BLOCK] float4 of dynamic shared memory (see trace_ray)
+  const size_t level_bytes = (size_t)(p.scene.depth > 0 ? p.scene.depth : 1) * 2 * RT_BLOCK * sizeof(float4);
+  if (g_blocks_per_sm == 0 || level_bytes != g_level_bytes) {
     int n = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, rt_render_kernel, RT_BLOCK, 0) != cudaSuccess || n < 1) n = 1;
+    cudaFuncSetAttribute(rt_render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RT_MAX_DEPTH * 2 * RT_BLOCK * 16);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, rt_render_kernel, RT_BLOCK, level_bytes) != cudaSuccess || n < 1) n = 1;
     g_blocks_per_sm = n;
+    g_level_bytes = level_bytes;
   }
   long long jobs = (long long)((p.width + 7) / 8) * ((p.height + 3) / 4) * 32;
   long long want = (jobs + RT_BLOCK - 1) / RT_BLOCK;
@@ -419,7 +415,7 @@ int rt_launch_render(const RenderParams &p, int sm_count, cudaStream_t stream) {
   if (want < grid) grid = want;
   if (grid < 1) grid = 1;
   cudaMemsetAsync(p.job_counter, 0, sizeof(unsigned int), stream);
-  rt_render_kernel<<<(unsigned)grid, RT_BLOCK, 0, stream>>>(p);
+  rt_render_kernel<<<(unsigned)grid, RT_BLOCK, level_bytes, stream>>>(p);
   return (int)cudaGetLastError();
 }
 
