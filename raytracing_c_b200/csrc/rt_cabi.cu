@@ -123,27 +123,24 @@ int build_device_scene(const Scene *scene, DeviceScene &ds) {
   const isize n_nodes = scene->bvh.nodes.len, n_slots = scene->triangles.len;
   if (n_nodes != bvh_n_internal_nodes(depth) || n_slots != bvh_n_leaf_nodes(depth) * RT_SIMD_WIDTH)
     return fail("scene: node/slot counts do not describe a complete 8-ary tree of depth %ld", (long)depth);
-  const isize n_leaves = n_slots / RT_SIMD_WIDTH;
 
   std::vector<float> nodes((size_t)n_nodes * 48);
   memcpy(nodes.data(), scene->bvh.nodes.data, nodes.size() * sizeof(float));
 
-  // leaf-major rows: p0.xyz, e1 = p1 - p0, e2 = p2 - p0.  The two edge vectors are the f32
+  // per slot: p0.xyz, e1 = p1 - p0, e2 = p2 - p0.  The two edge vectors are the f32
   // subtractions the reference redoes for every ray (raytracer.c:116-122); volatile keeps the
   // host compiler from doing them in any wider type
-  std::vector<float> leaf_pos((size_t)n_leaves * 72);
+  std::vector<float4> tri_pos((size_t)n_slots * 3);
   const float *px[3] = { scene->triangles.x[0], scene->triangles.y[0], scene->triangles.z[0] };
   const float *p1[3] = { scene->triangles.x[1], scene->triangles.y[1], scene->triangles.z[1] };
   const float *p2[3] = { scene->triangles.x[2], scene->triangles.y[2], scene->triangles.z[2] };
-  for (isize leaf = 0; leaf < n_leaves; leaf++)
-    for (int a = 0; a < 3; a++)
-      for (int j = 0; j < 8; j++) {
-        isize s = leaf * 8 + j;
-        volatile float e1 = p1[a][s] - px[a][s], e2 = p2[a][s] - px[a][s];
-        leaf_pos[(size_t)leaf * 72 + (size_t)(0 + a) * 8 + j] = px[a][s];
-        leaf_pos[(size_t)leaf * 72 + (size_t)(3 + a) * 8 + j] = e1;
-        leaf_pos[(size_t)leaf * 72 + (size_t)(6 + a) * 8 + j] = e2;
-      }
+  for (isize s = 0; s < n_slots; s++) {
+    volatile float e1[3], e2[3];
+    for (int a = 0; a < 3; a++) { e1[a] = p1[a][s] - px[a][s]; e2[a] = p2[a][s] - px[a][s]; }
+    tri_pos[(size_t)s * 3 + 0] = make_float4(px[0][s], px[1][s], px[2][s], e1[0]);
+    tri_pos[(size_t)s * 3 + 1] = make_float4(e1[1], e1[2], e2[0], e2[1]);
+    tri_pos[(size_t)s * 3 + 2] = make_float4(e2[2], 0.0f, 0.0f, 0.0f);
+  }
 
   // materials / textures, de-duplicated by host pointer
   std::map<const void *, int> material_index, texture_index;
@@ -225,7 +222,7 @@ int build_device_scene(const Scene *scene, DeviceScene &ds) {
 
   SceneDev &dev = ds.dev;
   if (upload(ds, nodes, &dev.nodes)) return 1;
-  if (upload(ds, leaf_pos, &dev.leaf_pos)) return 1;
+  if (upload(ds, tri_pos, &dev.tri_pos)) return 1;
   if (upload(ds, records, &dev.tri_rec)) return 1;
   if (upload(ds, materials, &dev.materials)) return 1;
   if (upload(ds, textures, &dev.textures)) return 1;

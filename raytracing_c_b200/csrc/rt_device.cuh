@@ -3,11 +3,13 @@
 // HBM layout (uploaded once per Scene, see rt_cabi.cu):
 //   nodes     f32[n_nodes][6][8]   exactly the host BVH_Node bytes (192 B): row r of
 //                                  node n is one 32-byte sector, lane j of an octet
-//                                  reads child j's bound -> 6 sector loads per visit.
-//   leaf_pos  f32[n_leaves][9][8]  the host's nine strided SoA arrays regrouped
-//                                  leaf-major (288 B contiguous per leaf instead of
-//                                  9 lines N*4 bytes apart); rows p0.x p0.y p0.z, then the
-//                                  edges e1 = p1-p0 and e2 = p2-p0 (x y z each).
+//                                  is child j's bound; a thread reads a node as twelve
+//                                  16-byte vectors (warp-uniform for coherent rays).
+//   tri_pos   float4[n_slots][3]   the host's nine strided SoA arrays regrouped per
+//                                  triangle slot (one thread tests a whole leaf, so a
+//                                  triangle is three 16-byte loads): (p0.xyz, e1.x)
+//                                  (e1.yz, e2.xy) (e2.z, 0, 0, 0) with the edges
+//                                  e1 = p1-p0 and e2 = p2-p0; leaf l = slots 8l..8l+7.
 //   tri_rec   float4[n_slots][7]   shading record (112 B): geometric normal, three
 //                                  vertex normals, tangent, bitangent, three UVs,
 //                                  material index (Triangle_AOS with the Shader
@@ -42,7 +44,7 @@ struct MaterialDev {
 
 struct SceneDev {
   const float       *nodes;
-  const float       *leaf_pos;
+  const float4      *tri_pos;
   const float4      *tri_rec;
   const MaterialDev *materials;
   const TextureDev  *textures;

@@ -99,62 +99,47 @@ __device__ __forceinline__ float min8(const float (&e)[8]) {
   return fminf(fminf(fminf(e[0], e[1]), fminf(e[2], e[3])), fminf(fminf(e[4], e[5]), fminf(e[6], e[7])));
 }
 
-// raytracer.c:84-188 for ONE triangle of a leaf; p0 and the edges e1 = p1 - p0, e2 = p2 - p0
-// (the same f32 subtractions raytracer.c:116-122 does per ray, done once at upload).
-// Strict <, ascending j: the lowest lane wins a tie inside the leaf and an earlier leaf wins
-// across leaves (raytracer.c:15-32 with eps 0, :159).
-__device__ __forceinline__ void triangle_test(float p0x, float p0y, float p0z, float e1x, float e1y, float e1z,
-                                              float e2x, float e2y, float e2z, float ox, float oy, float oz,
-                                              float dx, float dy, float dz, int slot,
-                                              float &hit_t, float &hit_u, float &hit_v, int &hit_slot) {
-  float pvx = dy * e2z - dz * e2y, pvy = dz * e2x - dx * e2z, pvz = dx * e2y - dy * e2x;
-  float det = e1x * pvx + e1y * pvy + e1z * pvz;
-  float inv_det = 1.0f / det;
-  float tvx = ox - p0x, tvy = oy - p0y, tvz = oz - p0z;
-  float qvx = tvy * e1z - tvz * e1y, qvy = tvz * e1x - tvx * e1z, qvz = tvx * e1y - tvy * e1x;
-  float u = inv_det * (tvx * pvx + tvy * pvy + tvz * pvz);
-  float v = inv_det * (dx * qvx + dy * qvy + dz * qvz);
-  float t = inv_det * (e2x * qvx + e2y * qvy + e2z * qvz);
-  bool miss = (u < -RT_EPS) | (u > 1 + RT_EPS) | (v < -RT_EPS) | (u + v > 1 + RT_EPS) | (t < RT_EPS);
-  // t <= 0 and NaN count as +inf (min_f32x8 with eps 0); NaN also fails the ordered compare
-  if (!miss && t > 0.0f && t < hit_t) { hit_t = t; hit_u = u; hit_v = v; hit_slot = slot; }
-}
-
 // per-thread slice of the level store: levels[(level - 1) * 2 + half][tid]
 #define RT_LEVELS(level, half) levels[(((level) - 1) * 2 + (half)) * RT_BLOCK]
 
-// raytracer.c:443-503: closest hit of one ray, one thread per ray.
+// raytracer.c:443-503: closest hit of one ray, one thread per ray; a WARP-COLLECTIVE call
+// (all 32 lanes enter; lanes without a ray pass active = false).
 // The reference recursion (8 entry distances per level on the C stack, up to 8 selection
 // rounds per node) is a flat loop here: the tree is a complete 8-ary heap, parent = (n-1)>>3;
 // the current node's entry distances live in registers, those of ancestors that still hold
 // untried candidates in shared memory, and `pending` (bit = level) lets a pop jump straight
 // to the nearest such ancestor.  Visit order and every compare are the reference's, so the
 // closest hit — ties included — is the same triangle slot.
-template <bool REGULAR>
-__device__ __forceinline__ void trace_ray(const SceneDev &sc, float4 *levels, float ox, float oy, float oz,
-                                          float dx, float dy, float dz, float ix, float iy, float iz,
-                                          float &hit_t, float &hit_u, float &hit_v,
-                                          int &hit_slot, unsigned &c_nodes, unsigned &c_leaves, unsigned &c_accepts) {
+// Shape: while-while with explicit reconvergence — lanes walk internal nodes until each
+// holds a leaf (or is finished), the warp syncs, then runs the triangle loop together.
+__device__ __forceinline__ void trace_ray(const SceneDev &sc, float4 *levels, bool active, float ox, float oy, float oz,
+                                          float dx, float dy, float dz,
+                                          float &hit_t, float &hit_u, float &hit_v, int &hit_slot,
+                                          unsigned &c_nodes, unsigned &c_leaves, unsigned &c_accepts) {
+  const float ix = 1.0f / dx, iy = 1.0f / dy, iz = 1.0f / dz;         // raytracer.c:198-202
+  // a zero direction component makes 1/d infinite and 0 * inf NaN: only then the slab test
+  // needs the exact MINPS/MAXPS operand-order rule (see child_entry)
+  const bool regular = (fabsf(ix) < CUDART_INF_F) & (fabsf(iy) < CUDART_INF_F) & (fabsf(iz) < CUDART_INF_F);
   int      node = 0, level = sc.depth;                                 // raytracer.c:501
   unsigned pending = 0;
-  bool     need_box = true;
+  bool     need_box = true, done = !active;
+  int      leaf = -1;
   float    e[8];
   hit_t = CUDART_INF_F; hit_u = 0; hit_v = 0; hit_slot = -1;
 
   for (;;) {
-    int leaf = -1;
-    // ---- walk internal nodes until this ray holds a leaf to test (or is finished); lanes
-    // that found one wait here so the warp runs the long triangle body together
-    for (;;) {
+    while (!done && leaf < 0) {
       if (need_box) {
-        node_entries<REGULAR>((const float4 *)(sc.nodes + (size_t)node * 48), ox, oy, oz, ix, iy, iz, hit_t, e);
+        const float4 *n4 = (const float4 *)(sc.nodes + (size_t)node * 48);
+        if (regular) node_entries<true >(n4, ox, oy, oz, ix, iy, iz, hit_t, e);
+        else         node_entries<false>(n4, ox, oy, oz, ix, iy, iz, hit_t, e);
         need_box = false;
         c_nodes++;
       }
       // raytracer.c:459-472: nearest untried child strictly below the current hit, lowest index on ties
       const float best = min8(e);
       if (!(best < hit_t)) {
-        if (pending == 0) break;
+        if (pending == 0) { done = true; break; }
         const int up = __ffs(pending) - 1;
         pending &= pending - 1;
         for (; level < up; level++) node = (node - 1) >> 3;
@@ -178,26 +163,39 @@ __device__ __forceinline__ void trace_ray(const SceneDev &sc, float4 *levels, fl
       level -= 1;
       need_box = true;
     }
-    if (leaf < 0) return;
+    __syncwarp();
+    if (__all_sync(0xffffffffu, done)) return;
 
-    // ---- raytracer.c:84-188: the eight triangles of the leaf (nine 32-byte rows)
-    {
-      const float4 *lp = (const float4 *)(sc.leaf_pos + (size_t)leaf * 72);
-      c_leaves++;
+    // ---- raytracer.c:84-188: the eight triangles of the leaf, three 16-byte loads each:
+    // p0 and the edges e1 = p1 - p0, e2 = p2 - p0 (the same f32 subtractions raytracer.c:116-122
+    // does per ray, done once at upload).  Strict <, ascending j: the lowest lane wins a tie
+    // inside the leaf and an earlier leaf wins across leaves (raytracer.c:15-32 with eps 0, :159).
+    if (leaf >= 0) {
+      const float4 *tp = sc.tri_pos + (size_t)leaf * 24;
       const float t_before = hit_t;
-      #pragma unroll
-      for (int h = 0; h < 2; h++) {
-        float4 p0x = __ldg(lp +  0 + h), p0y = __ldg(lp +  2 + h), p0z = __ldg(lp +  4 + h);
-        float4 e1x = __ldg(lp +  6 + h), e1y = __ldg(lp +  8 + h), e1z = __ldg(lp + 10 + h);
-        float4 e2x = __ldg(lp + 12 + h), e2y = __ldg(lp + 14 + h), e2z = __ldg(lp + 16 + h);
-        const int s0 = leaf * 8 + 4 * h;
-        triangle_test(p0x.x, p0y.x, p0z.x, e1x.x, e1y.x, e1z.x, e2x.x, e2y.x, e2z.x, ox, oy, oz, dx, dy, dz, s0 + 0, hit_t, hit_u, hit_v, hit_slot);
-        triangle_test(p0x.y, p0y.y, p0z.y, e1x.y, e1y.y, e1z.y, e2x.y, e2y.y, e2z.y, ox, oy, oz, dx, dy, dz, s0 + 1, hit_t, hit_u, hit_v, hit_slot);
-        triangle_test(p0x.z, p0y.z, p0z.z, e1x.z, e1y.z, e1z.z, e2x.z, e2y.z, e2z.z, ox, oy, oz, dx, dy, dz, s0 + 2, hit_t, hit_u, hit_v, hit_slot);
-        triangle_test(p0x.w, p0y.w, p0z.w, e1x.w, e1y.w, e1z.w, e2x.w, e2y.w, e2z.w, ox, oy, oz, dx, dy, dz, s0 + 3, hit_t, hit_u, hit_v, hit_slot);
+      c_leaves++;
+      #pragma unroll 1
+      for (int j = 0; j < 8; j++) {
+        const float4 A = __ldg(tp + 3 * j), B = __ldg(tp + 3 * j + 1), C = __ldg(tp + 3 * j + 2);
+        const float e1x = A.w, e1y = B.x, e1z = B.y, e2x = B.z, e2y = B.w, e2z = C.x;
+        float pvx = dy * e2z - dz * e2y, pvy = dz * e2x - dx * e2z, pvz = dx * e2y - dy * e2x;
+        float det = e1x * pvx + e1y * pvy + e1z * pvz;
+        float inv_det = 1.0f / det;
+        float tvx = ox - A.x, tvy = oy - A.y, tvz = oz - A.z;
+        float u = inv_det * (tvx * pvx + tvy * pvy + tvz * pvz);
+        // the reject mask is an OR (raytracer.c:137-152): a triangle that fails on u fails whatever v and t are
+        if ((u < -RT_EPS) | (u > 1 + RT_EPS)) continue;
+        float qvx = tvy * e1z - tvz * e1y, qvy = tvz * e1x - tvx * e1z, qvz = tvx * e1y - tvy * e1x;
+        float v = inv_det * (dx * qvx + dy * qvy + dz * qvz);
+        float t = inv_det * (e2x * qvx + e2y * qvy + e2z * qvz);
+        bool miss = (v < -RT_EPS) | (u + v > 1 + RT_EPS) | (t < RT_EPS);
+        // t <= 0 and NaN count as +inf (min_f32x8 with eps 0); NaN also fails the ordered compare
+        if (!miss && t > 0.0f && t < hit_t) { hit_t = t; hit_u = u; hit_v = v; hit_slot = leaf * 8 + j; }
       }
       if (hit_t < t_before) c_accepts++;
+      leaf = -1;
     }
+    __syncwarp();
   }
 }
 
@@ -283,16 +281,8 @@ rt_render_kernel(const __grid_constant__ RenderParams P) {
     // --------------------------------------------------------------------- trace
     float hit_t = CUDART_INF_F, hit_u = 0, hit_v = 0;
     int   slot = -1;
-    if (has_path) {
-      c_rays++;
-      // a zero direction component makes 1/d infinite and 0 * inf NaN: only then the slab test
-      // needs the exact MINPS/MAXPS operand-order rule (see child_entry)
-      const float ix = 1.0f / d.x, iy = 1.0f / d.y, iz = 1.0f / d.z;         // raytracer.c:198-202
-      const bool regular = (fabsf(ix) < CUDART_INF_F) & (fabsf(iy) < CUDART_INF_F) & (fabsf(iz) < CUDART_INF_F);
-      if (regular) trace_ray<true >(sc, levels, o.x, o.y, o.z, d.x, d.y, d.z, ix, iy, iz, hit_t, hit_u, hit_v, slot, c_nodes, c_leaves, c_accepts);
-      else         trace_ray<false>(sc, levels, o.x, o.y, o.z, d.x, d.y, d.z, ix, iy, iz, hit_t, hit_u, hit_v, slot, c_nodes, c_leaves, c_accepts);
-    }
-    __syncwarp();
+    if (has_path) c_rays++;
+    trace_ray(sc, levels, has_path, o.x, o.y, o.z, d.x, d.y, d.z, hit_t, hit_u, hit_v, slot, c_nodes, c_leaves, c_accepts);
 
     // --------------------------------------------------------------------- shade
     if (has_path) {
