@@ -66,7 +66,7 @@ struct State {
   float *d_accum = nullptr;   size_t accum_floats = 0;
   int   *d_hit_ids = nullptr; size_t hit_pixels = 0;
   unsigned long long *d_counters = nullptr;
-  unsigned int       *d_job = nullptr;
+  void  *d_workspace = nullptr; size_t workspace_bytes = 0;     // wavefront path queues (rt_render.cu)
   unsigned char *d_image = nullptr, *d_image2 = nullptr; size_t image_bytes = 0, image2_bytes = 0;
   unsigned char *h_pinned = nullptr; size_t pinned_bytes = 0;
   int    last_launches = 0;
@@ -257,17 +257,20 @@ int render_device_locked(const Scene *scene, isize width, isize height, isize s_
   if (width < 1 || height < 1) return fail("render: empty image");
   RenderParams p{};
   if (scene_on_device(scene, &p.scene)) return 1;
-  if (!g.d_job) CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&g.d_job), sizeof(unsigned int)));
+  const size_t want = rt_render_workspace_bytes((int)width, (int)height, (int)(s_end - s_begin), (int)max_bounces,
+                                                g.options.slice_samples);
+  if (g.workspace_bytes < want) {
+    CUDA_TRY(cudaStreamSynchronize(stream));      // an earlier launch may still read the old queues
+    if (grow(&g.d_workspace, &g.workspace_bytes, want)) return 1;
+  }
   p.width = (int)width; p.height = (int)height;
   p.sample_begin = (int)s_begin; p.sample_end = (int)s_end; p.max_bounces = (int)max_bounces;
   p.user_seed = seed;
   p.accumulate = accumulate;
   p.accum = d_accum; p.per_sample = d_per_sample; p.hit_ids = d_hit_ids;
   p.counters = d_counters;
-  p.job_counter = g.d_job;
-  int e = rt_launch_render(p, g.sm_count, stream);
+  int e = rt_launch_render(p, g.sm_count, g.d_workspace, g.workspace_bytes, stream, &g.last_launches);
   if (e) return fail("render kernel launch failed: %s", cudaGetErrorString((cudaError_t)e));
-  g.last_launches++;
   return 0;
 }
 
@@ -301,7 +304,7 @@ void rt_gpu_shutdown(void) {
   std::lock_guard<std::mutex> lock(g_mutex);
   for (auto &kv : g.scenes) release(kv.second);
   g.scenes.clear();
-  cudaFree(g.d_accum); cudaFree(g.d_hit_ids); cudaFree(g.d_counters); cudaFree(g.d_job);
+  cudaFree(g.d_accum); cudaFree(g.d_hit_ids); cudaFree(g.d_counters); cudaFree(g.d_workspace);
   cudaFree(g.d_image); cudaFree(g.d_image2);
   if (g.h_pinned) cudaFreeHost(g.h_pinned);
   if (g.ev0) cudaEventDestroy(g.ev0);

@@ -64,7 +64,6 @@ struct RenderParams {
   float    *per_sample;
   int      *hit_ids;
   unsigned long long *counters;
-  unsigned int       *job_counter;
 };
 
 __device__ __forceinline__ V3 mk3(float x, float y, float z) { V3 v; v.x = x; v.y = y; v.z = z; return v; }

@@ -5,7 +5,11 @@
 #include <cuda_runtime.h>
 #include "rt_device.cuh"
 
-int rt_launch_render(const RenderParams &p, int sm_count, cudaStream_t stream);
+// wavefront render of samples [p.sample_begin, p.sample_end) into p.accum; `workspace` holds the path queues
+// (rt_render_workspace_bytes; a smaller one only means more, smaller chunks).  *n_launches += kernels launched.
+size_t rt_render_workspace_bytes(int width, int height, int n_samples, int max_bounces, int slice_samples);
+int rt_launch_render(const RenderParams &p, int sm_count, void *workspace, size_t workspace_bytes,
+                     cudaStream_t stream, int *n_launches);
 int rt_launch_resolve(const float *accum, int width, int height, int samples, unsigned char *pixels,
                       int stride, int components, cudaStream_t stream);
 int rt_launch_denoise(const unsigned char *src, unsigned char *dst, int width, int height,
