@@ -102,15 +102,22 @@ __device__ __forceinline__ unsigned warp_append(unsigned *count, bool want, unsi
 }
 
 // ---------------------------------------------------------------------- trace
-// Persistent warps pull batches of 32 rays (the GPU form of the reference's atomic
-// 32x32 chunk queue, raytracer.c:619-627).  PRIMARY: the ray is generated from the path
-// id — a warp is one 8x4 pixel tile at one sample index, so its rays are coherent.
+// Persistent warps pull rays from the input queue (the GPU form of the reference's atomic
+// 32x32 chunk queue, raytracer.c:619-627) and keep their lanes full: whenever RT_REFILL_MIN
+// lanes have finished, those lanes append their results to the HIT / MISS queues and take the
+// next rays, while the others keep their walk state.  PRIMARY: the ray is generated from the
+// path id — 32 consecutive ids are one 8x4 pixel tile at one sample index, so rays are coherent.
+#ifndef RT_REFILL_MIN
+#define RT_REFILL_MIN 16
+#endif
+
 template <bool PRIMARY>
 __global__ void __launch_bounds__(RT_BLOCK, RT_TRACE_MIN_BLOCKS)
 rt_trace_kernel(const __grid_constant__ StageParams P) {
   extern __shared__ float4 level_store[];          // [depth][2][RT_BLOCK] entry distances of pending levels
   const SceneDev &sc = P.scene;
   const unsigned lane = threadIdx.x & 31u;
+  const unsigned lt_mask = (1u << lane) - 1u;
   float4 *levels = level_store + threadIdx.x;
   unsigned *counts = P.q.counts + P.bounce * Q_STRIDE;
   const unsigned n_in = PRIMARY ? P.n_paths : counts[Q_RAYS];
@@ -119,68 +126,100 @@ rt_trace_kernel(const __grid_constant__ StageParams P) {
   const float inv_w = 1.0f / (float)P.width, inv_h = 1.0f / (float)P.height;
   const float aspect = (float)P.width / (float)P.height;
 
+  RayWalk w;
+  w.done = true; w.leaf = -1;
+  bool     has_ray = false, exhausted = false;
+  unsigned q = 0;
+
   for (;;) {
-    unsigned base = 0;
-    if (lane == 0) base = atomicAdd(&counts[Q_FETCH], 32u);
-    base = __shfl_sync(RT_FULL, base, 0);
-    if (base >= n_in) break;
-    const unsigned q = base + lane;
-    bool active = q < n_in;
-
-    float ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = -1;
-    unsigned path = q;
-    uint32_t rng = 0;
-    int pixel = -1, ls = 0;
-    if (PRIMARY) {
-      int px, py;
-      path_pixel(P, q, px, py, ls);
-      active = active && px < P.width && py < P.height;
-      if (active) {
-        // raytracer.c:644-677; rand_a == rand_b; exact 1/sqrt instead of rsqrt_ps
-        const int s = P.sample0 + ls;
-        pixel = py * P.width + px;
-        float jit = hash12((float)px * 50.0f + (float)s, (float)py);
-        float ux = ((float)px + jit - 0.5f) * 2.0f * inv_w - 1.0f;
-        float uy = ((float)py + jit - 0.5f) * 2.0f * inv_h - 1.0f;
-        float cx = ux * aspect, cy = -uy, cz = -sc.focal_length;
-        float inv_len = 1.0f / __fsqrt_rn(cx * cx + cy * cy + cz * cz);
-        dx = (sc.view[0][0] * cx + sc.view[0][1] * cy + sc.view[0][2] * cz) * inv_len;
-        dy = (sc.view[1][0] * cx + sc.view[1][1] * cy + sc.view[1][2] * cz) * inv_len;
-        dz = (sc.view[2][0] * cx + sc.view[2][1] * cy + sc.view[2][2] * cz) * inv_len;
-        ox = sc.view[0][3]; oy = sc.view[1][3]; oz = sc.view[2][3];       // raytracer.c:612
-        rng = rt_path_seed((uint32_t)pixel, (uint32_t)s, P.user_seed);
+    const unsigned walking = __ballot_sync(RT_FULL, has_ray && !w.done);
+    if (walking == 0 || (!exhausted && __popc(~walking) >= RT_REFILL_MIN)) {
+      // ---- emit: finished lanes hand their path to the next stage
+      const bool fin = has_ray;        // every lane that is not walking and holds a ray has finished it
+      const bool is_hit = fin && !(walking >> lane & 1u) && w.hit_slot >= 0;
+      const bool is_miss = fin && !(walking >> lane & 1u) && w.hit_slot < 0;
+      if (__any_sync(RT_FULL, is_hit | is_miss)) {
+        unsigned path = q;
+        uint32_t rng = 0;
+        float4 tint = make_float4(1, 1, 1, 0), emis = make_float4(0, 0, 0, 0);
+        if (is_hit | is_miss) {
+          if (PRIMARY) {
+            int px, py, ls;
+            path_pixel(P, q, px, py, ls);
+            const int pixel = py * P.width + px;
+            rng = rt_path_seed((uint32_t)pixel, (uint32_t)(P.sample0 + ls), P.user_seed);
+            if (P.hit_ids && ls == 0) P.hit_ids[pixel] = w.hit_slot;
+          } else {
+            const float4 b = P.q.ray_b[q];
+            path = __float_as_uint(b.z);
+            rng  = __float_as_uint(b.w);
+            tint = P.q.ray_c[q];
+            emis = P.q.ray_d[q];
+          }
+        }
+        const unsigned hpos = warp_append(&counts[Q_HITS], is_hit, lane);
+        const unsigned mpos = warp_append(&counts[Q_MISSES], is_miss, lane);
+        if (is_hit) {
+          P.q.hit_a[hpos] = make_float4(w.ox, w.oy, w.oz, w.dx);
+          P.q.hit_b[hpos] = make_float4(w.dy, w.dz, __uint_as_float(path), __uint_as_float(rng));
+          P.q.hit_c[hpos] = tint;
+          P.q.hit_d[hpos] = emis;
+          P.q.hit_h[hpos] = make_float4(w.hit_t, w.hit_u, w.hit_v, __int_as_float(w.hit_slot));
+        }
+        if (is_miss) {
+          P.q.miss_a[mpos] = make_float4(w.dx, w.dy, w.dz, __uint_as_float(path));
+          P.q.miss_b[mpos] = tint;
+          P.q.miss_c[mpos] = emis;
+        }
+        if (is_hit | is_miss) has_ray = false;
       }
-    } else if (active) {
-      const float4 a = P.q.ray_a[q], b = P.q.ray_b[q];
-      ox = a.x; oy = a.y; oz = a.z; dx = a.w; dy = b.x; dz = b.y;
-      path = __float_as_uint(b.z);
-      rng  = __float_as_uint(b.w);
+      // ---- refill: every lane that is not walking takes the next ray of the queue
+      if (!exhausted) {
+        const unsigned idle = ~walking;
+        const unsigned need = (unsigned)__popc(idle);
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(&counts[Q_FETCH], need);
+        base = __shfl_sync(RT_FULL, base, 0);
+        exhausted = base + need >= n_in;
+        if (idle >> lane & 1u) {
+          q = base + (unsigned)__popc(idle & lt_mask);
+          bool ok = q < n_in;
+          float ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = -1;
+          if (PRIMARY) {
+            int px = 0, py = 0, ls = 0;
+            if (ok) path_pixel(P, q, px, py, ls);
+            ok = ok && px < P.width && py < P.height;
+            if (ok) {
+              // raytracer.c:644-677; rand_a == rand_b; exact 1/sqrt instead of rsqrt_ps
+              const int s = P.sample0 + ls;
+              float jit = hash12((float)px * 50.0f + (float)s, (float)py);
+              float ux = ((float)px + jit - 0.5f) * 2.0f * inv_w - 1.0f;
+              float uy = ((float)py + jit - 0.5f) * 2.0f * inv_h - 1.0f;
+              float cx = ux * aspect, cy = -uy, cz = -sc.focal_length;
+              float inv_len = 1.0f / __fsqrt_rn(cx * cx + cy * cy + cz * cz);
+              dx = (sc.view[0][0] * cx + sc.view[0][1] * cy + sc.view[0][2] * cz) * inv_len;
+              dy = (sc.view[1][0] * cx + sc.view[1][1] * cy + sc.view[1][2] * cz) * inv_len;
+              dz = (sc.view[2][0] * cx + sc.view[2][1] * cy + sc.view[2][2] * cz) * inv_len;
+              ox = sc.view[0][3]; oy = sc.view[1][3]; oz = sc.view[2][3];       // raytracer.c:612
+            }
+          } else if (ok) {
+            const float4 a = P.q.ray_a[q], b = P.q.ray_b[q];
+            ox = a.x; oy = a.y; oz = a.z; dx = a.w; dy = b.x; dz = b.y;
+          }
+          if (ok) {
+            walk_begin(w, sc, ox, oy, oz, dx, dy, dz);
+            has_ray = true;
+            c_rays++;
+          }
+        }
+      }
+      if (__ballot_sync(RT_FULL, has_ray) == 0) break;
     }
-    if (active) c_rays++;
 
-    float hit_t, hit_u, hit_v;
-    int   slot;
-    trace_ray(sc, levels, active, ox, oy, oz, dx, dy, dz, hit_t, hit_u, hit_v, slot, c_nodes, c_leaves, c_accepts);
-
-    if (PRIMARY && P.hit_ids && active && ls == 0) P.hit_ids[pixel] = slot;
-
-    float4 tint = make_float4(1, 1, 1, 0), emis = make_float4(0, 0, 0, 0);
-    if (!PRIMARY && active) { tint = P.q.ray_c[q]; emis = P.q.ray_d[q]; }
-    const bool is_hit = active && slot >= 0, is_miss = active && slot < 0;
-    const unsigned hpos = warp_append(&counts[Q_HITS], is_hit, lane);
-    const unsigned mpos = warp_append(&counts[Q_MISSES], is_miss, lane);
-    if (is_hit) {
-      P.q.hit_a[hpos] = make_float4(ox, oy, oz, dx);
-      P.q.hit_b[hpos] = make_float4(dy, dz, __uint_as_float(path), __uint_as_float(rng));
-      P.q.hit_c[hpos] = tint;
-      P.q.hit_d[hpos] = emis;
-      P.q.hit_h[hpos] = make_float4(hit_t, hit_u, hit_v, __int_as_float(slot));
-    }
-    if (is_miss) {
-      P.q.miss_a[mpos] = make_float4(dx, dy, dz, __uint_as_float(path));
-      P.q.miss_b[mpos] = tint;
-      P.q.miss_c[mpos] = emis;
-    }
+    walk_to_leaf(w, sc, levels, c_nodes);
+    __syncwarp();
+    walk_leaf(w, sc, c_leaves, c_accepts);
+    __syncwarp();
   }
 
   if (P.counters) {

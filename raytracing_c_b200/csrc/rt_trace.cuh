@@ -71,100 +71,107 @@ __device__ __forceinline__ float min8(const float (&e)[8]) {
 // per-thread slice of the level store: levels[(level - 1) * 2 + half][tid]
 #define RT_LEVELS(level, half) levels[(((level) - 1) * 2 + (half)) * RT_BLOCK]
 
-// raytracer.c:443-503: closest hit of one ray, one thread per ray; a WARP-COLLECTIVE call
-// (all 32 lanes enter; lanes without a ray pass active = false).
+// raytracer.c:443-503: closest hit of one ray, one thread per ray, as a resumable walk.
 // The reference recursion (8 entry distances per level on the C stack, up to 8 selection
 // rounds per node) is a flat loop here: the tree is a complete 8-ary heap, parent = (n-1)>>3;
 // the current node's entry distances live in registers, those of ancestors that still hold
 // untried candidates in shared memory, and `pending` (bit = level) lets a pop jump straight
 // to the nearest such ancestor.  Visit order and every compare are the reference's, so the
 // closest hit — ties included — is the same triangle slot.
-// Shape: while-while with explicit reconvergence — lanes walk internal nodes until each
-// holds a leaf (or is finished), the warp syncs, then runs the triangle loop together.
-__device__ __forceinline__ void trace_ray(const SceneDev &sc, float4 *levels, bool active, float ox, float oy, float oz,
-                                          float dx, float dy, float dz,
-                                          float &hit_t, float &hit_u, float &hit_v, int &hit_slot,
-                                          unsigned &c_nodes, unsigned &c_leaves, unsigned &c_accepts) {
-  const float ix = 1.0f / dx, iy = 1.0f / dy, iz = 1.0f / dz;         // raytracer.c:198-202
+// Shape: while-while with explicit reconvergence, driven by the caller (rt_trace_kernel):
+//   walk_to_leaf  lanes walk internal nodes until each holds a leaf or is done   (divergent)
+//   __syncwarp
+//   walk_leaf     the warp runs the triangle loop together
+struct RayWalk {
+  float ox, oy, oz, dx, dy, dz, ix, iy, iz;
+  float hit_t, hit_u, hit_v;
+  int   hit_slot;
+  int   node, level, leaf;
+  unsigned pending;
+  float e[8];
+  bool  need_box, regular, done;
+};
+
+__device__ __forceinline__ void walk_begin(RayWalk &w, const SceneDev &sc, float ox, float oy, float oz,
+                                           float dx, float dy, float dz) {
+  w.ox = ox; w.oy = oy; w.oz = oz; w.dx = dx; w.dy = dy; w.dz = dz;
+  w.ix = 1.0f / dx; w.iy = 1.0f / dy; w.iz = 1.0f / dz;                // raytracer.c:198-202
   // a zero direction component makes 1/d infinite and 0 * inf NaN: only then the slab test
   // needs the exact MINPS/MAXPS operand-order rule (see child_entry)
-  const bool regular = (fabsf(ix) < CUDART_INF_F) & (fabsf(iy) < CUDART_INF_F) & (fabsf(iz) < CUDART_INF_F);
-  int      node = 0, level = sc.depth;                                 // raytracer.c:501
-  unsigned pending = 0;
-  bool     need_box = true, done = !active;
-  int      leaf = -1;
-  float    e[8];
-  hit_t = CUDART_INF_F; hit_u = 0; hit_v = 0; hit_slot = -1;
+  w.regular = (fabsf(w.ix) < CUDART_INF_F) & (fabsf(w.iy) < CUDART_INF_F) & (fabsf(w.iz) < CUDART_INF_F);
+  w.node = 0; w.level = sc.depth;                                       // raytracer.c:501
+  w.pending = 0; w.leaf = -1;
+  w.need_box = true; w.done = false;
+  w.hit_t = CUDART_INF_F; w.hit_u = 0; w.hit_v = 0; w.hit_slot = -1;
+}
 
-  for (;;) {
-    while (!done && leaf < 0) {
-      if (need_box) {
-        const float4 *n4 = (const float4 *)(sc.nodes + (size_t)node * 48);
-        if (regular) node_entries<true >(n4, ox, oy, oz, ix, iy, iz, hit_t, e);
-        else         node_entries<false>(n4, ox, oy, oz, ix, iy, iz, hit_t, e);
-        need_box = false;
-        c_nodes++;
-      }
-      // raytracer.c:459-472: nearest untried child strictly below the current hit, lowest index on ties
-      const float best = min8(e);
-      if (!(best < hit_t)) {
-        if (pending == 0) { done = true; break; }
-        const int up = __ffs(pending) - 1;
-        pending &= pending - 1;
-        for (; level < up; level++) node = (node - 1) >> 3;
-        float4 a = RT_LEVELS(level, 0), b = RT_LEVELS(level, 1);
-        e[0] = a.x; e[1] = a.y; e[2] = a.z; e[3] = a.w; e[4] = b.x; e[5] = b.y; e[6] = b.z; e[7] = b.w;
-        continue;
-      }
-      int pick = 7;
-      #pragma unroll
-      for (int j = 6; j >= 0; j--) pick = (e[j] == best) ? j : pick;
-      #pragma unroll
-      for (int j = 0; j < 8; j++) e[j] = (j == pick) ? CUDART_INF_F : e[j];       // raytracer.c:481
-      const int child = 8 * node + 1 + pick;
-      if (level == 1) { leaf = child - sc.n_internal; break; }
-      if (min8(e) < hit_t) {                         // other candidates remain: remember this level
-        RT_LEVELS(level, 0) = make_float4(e[0], e[1], e[2], e[3]);
-        RT_LEVELS(level, 1) = make_float4(e[4], e[5], e[6], e[7]);
-        pending |= 1u << level;
-      }
-      node = child;
-      level -= 1;
-      need_box = true;
+__device__ __forceinline__ void walk_to_leaf(RayWalk &w, const SceneDev &sc, float4 *levels, unsigned &c_nodes) {
+  float (&e)[8] = w.e;
+  while (!w.done && w.leaf < 0) {
+    if (w.need_box) {
+      const float4 *n4 = (const float4 *)(sc.nodes + (size_t)w.node * 48);
+      if (w.regular) node_entries<true >(n4, w.ox, w.oy, w.oz, w.ix, w.iy, w.iz, w.hit_t, e);
+      else           node_entries<false>(n4, w.ox, w.oy, w.oz, w.ix, w.iy, w.iz, w.hit_t, e);
+      w.need_box = false;
+      c_nodes++;
     }
-    __syncwarp();
-    if (__all_sync(0xffffffffu, done)) return;
-
-    // ---- raytracer.c:84-188: the eight triangles of the leaf, three 16-byte loads each:
-    // p0 and the edges e1 = p1 - p0, e2 = p2 - p0 (the same f32 subtractions raytracer.c:116-122
-    // does per ray, done once at upload).  Strict <, ascending j: the lowest lane wins a tie
-    // inside the leaf and an earlier leaf wins across leaves (raytracer.c:15-32 with eps 0, :159).
-    if (leaf >= 0) {
-      const float4 *tp = sc.tri_pos + (size_t)leaf * 24;
-      const float t_before = hit_t;
-      c_leaves++;
+    // raytracer.c:459-472: nearest untried child strictly below the current hit, lowest index on ties
+    const float best = min8(e);
+    if (!(best < w.hit_t)) {
+      if (w.pending == 0) { w.done = true; break; }
+      const int up = __ffs(w.pending) - 1;
+      w.pending &= w.pending - 1;
       #pragma unroll 1
-      for (int j = 0; j < 8; j++) {
-        const float4 A = __ldg(tp + 3 * j), B = __ldg(tp + 3 * j + 1), C = __ldg(tp + 3 * j + 2);
-        const float e1x = A.w, e1y = B.x, e1z = B.y, e2x = B.z, e2y = B.w, e2z = C.x;
-        float pvx = dy * e2z - dz * e2y, pvy = dz * e2x - dx * e2z, pvz = dx * e2y - dy * e2x;
-        float det = e1x * pvx + e1y * pvy + e1z * pvz;
-        float inv_det = 1.0f / det;
-        float tvx = ox - A.x, tvy = oy - A.y, tvz = oz - A.z;
-        float u = inv_det * (tvx * pvx + tvy * pvy + tvz * pvz);
-        // the reject mask is an OR (raytracer.c:137-152): a triangle that fails on u fails whatever v and t are
-        if ((u < -RT_EPS) | (u > 1 + RT_EPS)) continue;
-        float qvx = tvy * e1z - tvz * e1y, qvy = tvz * e1x - tvx * e1z, qvz = tvx * e1y - tvy * e1x;
-        float v = inv_det * (dx * qvx + dy * qvy + dz * qvz);
-        float t = inv_det * (e2x * qvx + e2y * qvy + e2z * qvz);
-        bool miss = (v < -RT_EPS) | (u + v > 1 + RT_EPS) | (t < RT_EPS);
-        // t <= 0 and NaN count as +inf (min_f32x8 with eps 0); NaN also fails the ordered compare
-        if (!miss && t > 0.0f && t < hit_t) { hit_t = t; hit_u = u; hit_v = v; hit_slot = leaf * 8 + j; }
-      }
-      if (hit_t < t_before) c_accepts++;
-      leaf = -1;
+      for (; w.level < up; w.level++) w.node = (w.node - 1) >> 3;
+      float4 a = RT_LEVELS(w.level, 0), b = RT_LEVELS(w.level, 1);
+      e[0] = a.x; e[1] = a.y; e[2] = a.z; e[3] = a.w; e[4] = b.x; e[5] = b.y; e[6] = b.z; e[7] = b.w;
+      continue;
     }
-    __syncwarp();
+    int pick = 7;
+    #pragma unroll
+    for (int j = 6; j >= 0; j--) pick = (e[j] == best) ? j : pick;
+    #pragma unroll
+    for (int j = 0; j < 8; j++) e[j] = (j == pick) ? CUDART_INF_F : e[j];       // raytracer.c:481
+    const int child = 8 * w.node + 1 + pick;
+    if (w.level == 1) { w.leaf = child - sc.n_internal; break; }
+    if (min8(e) < w.hit_t) {                         // other candidates remain: remember this level
+      RT_LEVELS(w.level, 0) = make_float4(e[0], e[1], e[2], e[3]);
+      RT_LEVELS(w.level, 1) = make_float4(e[4], e[5], e[6], e[7]);
+      w.pending |= 1u << w.level;
+    }
+    w.node = child;
+    w.level -= 1;
+    w.need_box = true;
   }
 }
 
+// raytracer.c:84-188: the eight triangles of the leaf, three 16-byte loads each:
+// p0 and the edges e1 = p1 - p0, e2 = p2 - p0 (the same f32 subtractions raytracer.c:116-122
+// does per ray, done once at upload).  Strict <, ascending j: the lowest lane wins a tie
+// inside the leaf and an earlier leaf wins across leaves (raytracer.c:15-32 with eps 0, :159).
+__device__ __forceinline__ void walk_leaf(RayWalk &w, const SceneDev &sc, unsigned &c_leaves, unsigned &c_accepts) {
+  if (w.leaf < 0) return;
+  const float4 *tp = sc.tri_pos + (size_t)w.leaf * 24;
+  const float t_before = w.hit_t;
+  c_leaves++;
+  #pragma unroll 1
+  for (int j = 0; j < 8; j++) {
+    const float4 A = __ldg(tp + 3 * j), B = __ldg(tp + 3 * j + 1), C = __ldg(tp + 3 * j + 2);
+    const float e1x = A.w, e1y = B.x, e1z = B.y, e2x = B.z, e2y = B.w, e2z = C.x;
+    float pvx = w.dy * e2z - w.dz * e2y, pvy = w.dz * e2x - w.dx * e2z, pvz = w.dx * e2y - w.dy * e2x;
+    float det = e1x * pvx + e1y * pvy + e1z * pvz;
+    float inv_det = 1.0f / det;
+    float tvx = w.ox - A.x, tvy = w.oy - A.y, tvz = w.oz - A.z;
+    float u = inv_det * (tvx * pvx + tvy * pvy + tvz * pvz);
+    // the reject mask is an OR (raytracer.c:137-152): a triangle that fails on u fails whatever v and t are
+    if ((u < -RT_EPS) | (u > 1 + RT_EPS)) continue;
+    float qvx = tvy * e1z - tvz * e1y, qvy = tvz * e1x - tvx * e1z, qvz = tvx * e1y - tvy * e1x;
+    float v = inv_det * (w.dx * qvx + w.dy * qvy + w.dz * qvz);
+    float t = inv_det * (e2x * qvx + e2y * qvy + e2z * qvz);
+    bool miss = (v < -RT_EPS) | (u + v > 1 + RT_EPS) | (t < RT_EPS);
+    // t <= 0 and NaN count as +inf (min_f32x8 with eps 0); NaN also fails the ordered compare
+    if (!miss && t > 0.0f && t < w.hit_t) { w.hit_t = t; w.hit_u = u; w.hit_v = v; w.hit_slot = w.leaf * 8 + j; }
+  }
+  if (w.hit_t < t_before) c_accepts++;
+  w.leaf = -1;
+}
