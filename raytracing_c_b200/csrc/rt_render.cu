@@ -35,6 +35,9 @@
 #ifndef RT_TRACE_MIN_BLOCKS
 #define RT_TRACE_MIN_BLOCKS 3
 #endif
+#ifndef RT_TRACE_LANE_BLOCKS
+#define RT_TRACE_LANE_BLOCKS 2
+#endif
 #define RT_FULL 0xffffffffu
 
 // counts[bounce][...]: queue lengths written by one stage and read by the next
@@ -216,9 +219,15 @@ rt_trace_kernel(const __grid_constant__ StageParams P) {
       if (__ballot_sync(RT_FULL, has_ray) == 0) break;
     }
 
-    walk_to_leaf(w, sc, levels, c_nodes);
-    __syncwarp();
-    walk_leaf(w, sc, c_leaves, c_accepts);
+    // ---- one step for the majority: node steps and leaf tests are different code, so the warp runs
+    // whichever more lanes wait for and the others keep their state for a later turn
+    const unsigned want_leaf = __ballot_sync(RT_FULL, w.leaf >= 0);
+    const unsigned want_node = __ballot_sync(RT_FULL, has_ray && !w.done && w.leaf < 0);
+    if (__popc(want_node) >= __popc(want_leaf)) {
+      if (want_node >> lane & 1u) walk_node_step(w, sc, levels, c_nodes);
+    } else {
+      walk_leaf(w, sc, c_leaves, c_accepts);
+    }
     __syncwarp();
   }
 
@@ -407,6 +416,17 @@ size_t rt_render_workspace_bytes(int width, int height, int n_samples, int max_b
 
 static int g_trace_blocks_per_sm = 0;
 static size_t g_level_bytes = 0;
+// Two chunks are kept in flight on two helper streams: the low-occupancy tail of one chunk
+// (late bounces hold few rays) overlaps the full-width kernels of the next.
+static cudaStream_t g_lane_stream[2] = { nullptr, nullptr };
+static cudaEvent_t  g_ev_fork = nullptr, g_ev_chunk[2] = { nullptr, nullptr }, g_ev_acc[2] = { nullptr, nullptr };
+
+static void bind_queues(PathQueues &q, char *w, size_t cb, size_t cap) {
+  q.counts = reinterpret_cast<unsigned *>(w); w += cb;
+  float4 **arrays[] = { &q.ray_a, &q.ray_b, &q.ray_c, &q.ray_d, &q.hit_a, &q.hit_b, &q.hit_c,
+                        &q.hit_d, &q.hit_h, &q.miss_a, &q.miss_b, &q.miss_c, &q.rad };
+  for (float4 **a : arrays) { *a = reinterpret_cast<float4 *>(w); w += cap * sizeof(float4); }
+}
 
 int rt_launch_render(const RenderParams &p, int sm_count, void *workspace, size_t workspace_bytes,
                      cudaStream_t stream, int *n_launches) {
@@ -416,7 +436,7 @@ int rt_launch_render(const RenderParams &p, int sm_count, void *workspace, size_
     if (!p.accumulate) cudaMemsetAsync(p.accum, 0, (size_t)p.width * p.height * 3 * sizeof(float), stream);
     return (int)cudaGetLastError();
   }
-  // level store: [depth][2][RT_BLOCK] float4 of dynamic shared memory (see trace_ray)
+  // level store: [depth][2][RT_BLOCK] float4 of dynamic shared memory (see rt_trace.cuh)
   const size_t level_bytes = (size_t)(p.scene.depth > 0 ? p.scene.depth : 1) * 2 * RT_BLOCK * sizeof(float4);
   if (g_trace_blocks_per_sm == 0 || level_bytes != g_level_bytes) {
     int n = 0;
@@ -425,6 +445,14 @@ int rt_launch_render(const RenderParams &p, int sm_count, void *workspace, size_
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, rt_trace_kernel<false>, RT_BLOCK, level_bytes) != cudaSuccess || n < 1) n = 1;
     g_trace_blocks_per_sm = n;
     g_level_bytes = level_bytes;
+  }
+  if (!g_ev_fork) {
+    for (int i = 0; i < 2; i++) {
+      if (cudaStreamCreateWithFlags(&g_lane_stream[i], cudaStreamNonBlocking) != cudaSuccess) return (int)cudaGetLastError();
+      cudaEventCreateWithFlags(&g_ev_chunk[i], cudaEventDisableTiming);
+      cudaEventCreateWithFlags(&g_ev_acc[i], cudaEventDisableTiming);
+    }
+    cudaEventCreateWithFlags(&g_ev_fork, cudaEventDisableTiming);
   }
 
   StageParams P{};
@@ -438,43 +466,60 @@ int rt_launch_render(const RenderParams &p, int sm_count, void *workspace, size_
   P.per_sample_stride = n_total;
   P.counters = p.counters;
 
+  // chunking: the workspace is one set of queues when the whole job fits in it, else two halves
   const size_t per_sample = (size_t)P.tiles_x * (size_t)P.tiles_y * 32;
   const size_t cb = counts_bytes(p.max_bounces);
   if (workspace_bytes < cb + per_sample * RT_PATH_BYTES) return (int)cudaErrorMemoryAllocation;
-  size_t cap = (workspace_bytes - cb) / RT_PATH_BYTES;             // paths the workspace holds
-  int chunk = (int)(cap / per_sample < (size_t)n_total ? cap / per_sample : (size_t)n_total);
-  cap = (size_t)chunk * per_sample;
-  {
-    char *w = static_cast<char *>(workspace);
-    P.q.counts = reinterpret_cast<unsigned *>(w); w += cb;
-    float4 **arrays[] = { &P.q.ray_a, &P.q.ray_b, &P.q.ray_c, &P.q.ray_d, &P.q.hit_a, &P.q.hit_b, &P.q.hit_c,
-                          &P.q.hit_d, &P.q.hit_h, &P.q.miss_a, &P.q.miss_b, &P.q.miss_c, &P.q.rad };
-    for (float4 **a : arrays) { *a = reinterpret_cast<float4 *>(w); w += cap * sizeof(float4); }
+  const size_t half_bytes = (workspace_bytes / 2) & ~(size_t)255;
+  int    lanes = 1;
+  size_t cap = (workspace_bytes - cb) / RT_PATH_BYTES;             // paths one set of queues holds
+  if (cap / per_sample < (size_t)n_total && half_bytes >= cb + per_sample * RT_PATH_BYTES) {
+    lanes = 2;
+    cap = (half_bytes - cb) / RT_PATH_BYTES;
   }
+  const int chunk = (int)(cap / per_sample < (size_t)n_total ? cap / per_sample : (size_t)n_total);
+  cap = (size_t)chunk * per_sample;
+  PathQueues queues[2];
+  for (int i = 0; i < lanes; i++) bind_queues(queues[i], static_cast<char *>(workspace) + (size_t)i * half_bytes, cb, cap);
 
-  const unsigned trace_grid = (unsigned)(sm_count * g_trace_blocks_per_sm);
+  // persistent trace grids: with two chunks in flight each takes 2 of the (usually 3) block slots of an SM,
+  // so a kernel of the other chunk always finds room instead of queueing behind a full machine
+  int per_sm = g_trace_blocks_per_sm;
+  if (lanes == 2 && per_sm > RT_TRACE_LANE_BLOCKS) per_sm = RT_TRACE_LANE_BLOCKS;
+  const unsigned trace_grid = (unsigned)(sm_count * per_sm);
   const unsigned flat_grid  = (unsigned)(sm_count * 8);
-  int launches = 0;
-  for (int s0 = p.sample_begin; s0 < p.sample_end; s0 += chunk) {
+  int launches = 0, k = 0;
+  cudaEventRecord(g_ev_fork, stream);
+  for (int s0 = p.sample_begin; s0 < p.sample_end; s0 += chunk, k++) {
+    const int lane = k % lanes;
+    cudaStream_t st = g_lane_stream[lane];
+    // this lane's queues are free once the accumulate of the chunk that used them last has run
+    cudaStreamWaitEvent(st, k < lanes ? g_ev_fork : g_ev_acc[lane], 0);
+
     const int S = (p.sample_end - s0 < chunk) ? p.sample_end - s0 : chunk;
+    P.q = queues[lane];
     P.sample0 = s0; P.n_samples = S;
     P.n_paths = (unsigned)(per_sample * (size_t)S);
     P.accumulate = (p.accumulate || s0 > p.sample_begin) ? 1 : 0;
     P.per_sample_offset = s0 - p.sample_begin;
     P.hit_ids = (s0 == p.sample_begin) ? p.hit_ids : nullptr;
-    cudaMemsetAsync(P.q.counts, 0, cb, stream);
+    cudaMemsetAsync(P.q.counts, 0, cb, st);
     P.bounce = 0;
-    rt_trace_kernel<true><<<trace_grid, RT_BLOCK, level_bytes, stream>>>(P);
+    rt_trace_kernel<true><<<trace_grid, RT_BLOCK, level_bytes, st>>>(P);
     launches++;
     for (int b = 0; b < p.max_bounces; b++) {
       P.bounce = b;
-      if (b > 0) { rt_trace_kernel<false><<<trace_grid, RT_BLOCK, level_bytes, stream>>>(P); launches++; }
-      rt_miss_kernel<<<flat_grid, 256, 0, stream>>>(P);
-      rt_shade_kernel<<<flat_grid, 256, 0, stream>>>(P);
+      if (b > 0) { rt_trace_kernel<false><<<trace_grid, RT_BLOCK, level_bytes, st>>>(P); launches++; }
+      rt_miss_kernel<<<flat_grid, 256, 0, st>>>(P);
+      rt_shade_kernel<<<flat_grid, 256, 0, st>>>(P);
       launches += 2;
     }
+    // the per-pixel sums run on the caller's stream, one chunk after the other, in sample order
+    cudaEventRecord(g_ev_chunk[lane], st);
+    cudaStreamWaitEvent(stream, g_ev_chunk[lane], 0);
     rt_accumulate_kernel<<<flat_grid, 256, 0, stream>>>(P);
     launches++;
+    cudaEventRecord(g_ev_acc[lane], stream);
   }
   if (n_launches) *n_launches += launches;
   return (int)cudaGetLastError();

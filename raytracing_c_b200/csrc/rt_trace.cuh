@@ -18,49 +18,74 @@
 #define RT_BLOCK 256
 #endif
 
-// raytracer.c:190-230 for ONE child box.
-// `regular` = all three reciprocal direction components are finite.  Then no product
-// below can be NaN (finite * finite), so MINPS/MAXPS' "second operand when unordered"
-// rule never fires and the hardware FMNMX gives the same value (a zero's sign can
-// differ, but `enter` is >= EPS and `leave` is only compared).  Otherwise the exact
-// operand-order selects are used (0 * inf lanes, raytracer.c:212-225).
-template <bool REGULAR>
-__device__ __forceinline__ float child_entry(float lox, float loy, float loz, float hix, float hiy, float hiz,
-                                             float ox, float oy, float oz, float ix, float iy, float iz, float t_max) {
-  float ax = (lox - ox) * ix;
-  float ay = (loy - oy) * iy;
-  float az = (loz - oz) * iz;
-  float bx = (hix - ox) * ix;
-  float by = (hiy - oy) * iy;
-  float bz = (hiz - oz) * iz;
-  float enter, leave;
-  if (REGULAR) {
-    enter = fmaxf(RT_EPS, fmaxf(fminf(ax, bx), fmaxf(fminf(ay, by), fminf(az, bz))));
-    leave = fminf(t_max,  fminf(fmaxf(ax, bx), fminf(fmaxf(ay, by), fmaxf(az, bz))));
-  } else {
-    float nx = sel_min(ax, bx), ny = sel_min(ay, by), nz = sel_min(az, bz);
-    float fx = sel_max(ax, bx), fy = sel_max(ay, by), fz = sel_max(az, bz);
-    enter = sel_max(RT_EPS, sel_max(nx, sel_max(ny, nz)));
-    leave = sel_min(t_max,  sel_min(fx, sel_min(fy, fz)));
-  }
+// raytracer.c:190-230 for ONE child box, general form: the reference's nested MINPS/MAXPS with
+// their "second operand when unordered" rule, as operand-order selects.  Needed only when a
+// reciprocal direction component is infinite (0 * inf = NaN lanes, raytracer.c:212-225).
+__device__ __forceinline__ float child_entry_any(float lox, float loy, float loz, float hix, float hiy, float hiz,
+                                                 float ox, float oy, float oz, float ix, float iy, float iz, float t_max) {
+  float ax = (lox - ox) * ix, ay = (loy - oy) * iy, az = (loz - oz) * iz;
+  float bx = (hix - ox) * ix, by = (hiy - oy) * iy, bz = (hiz - oz) * iz;
+  float nx = sel_min(ax, bx), ny = sel_min(ay, by), nz = sel_min(az, bz);
+  float fx = sel_max(ax, bx), fy = sel_max(ay, by), fz = sel_max(az, bz);
+  float enter = sel_max(RT_EPS, sel_max(nx, sel_max(ny, nz)));
+  float leave = sel_min(t_max,  sel_min(fx, sel_min(fy, fz)));
+  return (enter >= leave) ? CUDART_INF_F : enter;
+}
+
+// The same box for a REGULAR ray (all three reciprocals finite, so every product is finite and
+// no NaN rule can fire).  IEEE subtraction and multiplication are monotonic and lo <= hi for every
+// box scene_init writes (EPSILON-inflated, or all-zero padding), so (lo - o) * i <= (hi - o) * i
+// when i > 0 and >= when i < 0: min(a, b) / max(a, b) of the reference are known from the sign
+// of i alone.  The caller hands in the near and far plane per axis; the values — and therefore
+// enter, leave and the compare — are the reference's (a zero's sign can differ, but enter >= EPS
+// and leave is only compared).
+__device__ __forceinline__ float child_entry_regular(float nx, float ny, float nz, float fx, float fy, float fz,
+                                                     float ox, float oy, float oz, float ix, float iy, float iz, float t_max) {
+  float enter = fmaxf(fmaxf((nx - ox) * ix, (ny - oy) * iy), fmaxf((nz - oz) * iz, RT_EPS));
+  float leave = fminf(fminf((fx - ox) * ix, (fy - oy) * iy), fminf((fz - oz) * iz, t_max));
   return (enter >= leave) ? CUDART_INF_F : enter;
 }
 
 // raytracer.c:190-230, ray_aabbs_hit_8: the eight children of one node, entry distance or +inf.
 // A node is six 32-byte rows (min x/y/z, max x/y/z; child j in column j): twelve 16-byte loads,
-// warp-uniform for coherent rays.
-template <bool REGULAR>
-__device__ __forceinline__ void node_entries(const float4 *__restrict__ n4, float ox, float oy, float oz,
-                                             float ix, float iy, float iz, float t_max, float (&e)[8]) {
+// warp-uniform for coherent rays.  near_rows packs, per axis, which row holds the near plane
+// (bit a set = direction negative on axis a = the max row is nearer).
+__device__ __forceinline__ void node_entries_regular(const float4 *__restrict__ n4, unsigned near_rows,
+                                                     float ox, float oy, float oz, float ix, float iy, float iz,
+                                                     float t_max, float (&e)[8]) {
+  const int nxr = (near_rows & 1u) ? 6 : 0, nyr = (near_rows & 2u) ? 8 : 2, nzr = (near_rows & 4u) ? 10 : 4;
+  const int fxr = 6 - nxr, fyr = 10 - nyr, fzr = 14 - nzr;
   #pragma unroll
   for (int h = 0; h < 2; h++) {
-    float4 lx = __ldg(n4 + 0 + h), ly = __ldg(n4 + 2 + h), lz = __ldg(n4 + 4 + h);
-    float4 hx = __ldg(n4 + 6 + h), hy = __ldg(n4 + 8 + h), hz = __ldg(n4 + 10 + h);
-    e[4 * h + 0] = child_entry<REGULAR>(lx.x, ly.x, lz.x, hx.x, hy.x, hz.x, ox, oy, oz, ix, iy, iz, t_max);
-    e[4 * h + 1] = child_entry<REGULAR>(lx.y, ly.y, lz.y, hx.y, hy.y, hz.y, ox, oy, oz, ix, iy, iz, t_max);
-    e[4 * h + 2] = child_entry<REGULAR>(lx.z, ly.z, lz.z, hx.z, hy.z, hz.z, ox, oy, oz, ix, iy, iz, t_max);
-    e[4 * h + 3] = child_entry<REGULAR>(lx.w, ly.w, lz.w, hx.w, hy.w, hz.w, ox, oy, oz, ix, iy, iz, t_max);
+    float4 nx = __ldg(n4 + nxr + h), ny = __ldg(n4 + nyr + h), nz = __ldg(n4 + nzr + h);
+    float4 fx = __ldg(n4 + fxr + h), fy = __ldg(n4 + fyr + h), fz = __ldg(n4 + fzr + h);
+    e[4 * h + 0] = child_entry_regular(nx.x, ny.x, nz.x, fx.x, fy.x, fz.x, ox, oy, oz, ix, iy, iz, t_max);
+    e[4 * h + 1] = child_entry_regular(nx.y, ny.y, nz.y, fx.y, fy.y, fz.y, ox, oy, oz, ix, iy, iz, t_max);
+    e[4 * h + 2] = child_entry_regular(nx.z, ny.z, nz.z, fx.z, fy.z, fz.z, ox, oy, oz, ix, iy, iz, t_max);
+    e[4 * h + 3] = child_entry_regular(nx.w, ny.w, nz.w, fx.w, fy.w, fz.w, ox, oy, oz, ix, iy, iz, t_max);
   }
+}
+
+// out of line and by value: the rare path must not cost the common one registers or code
+struct Entries8 { float4 lo, hi; };
+__device__ __noinline__ Entries8 node_entries_any(const float4 *__restrict__ n4, float ox, float oy, float oz,
+                                                  float ix, float iy, float iz, float t_max) {
+  Entries8 r;
+  {
+    float4 lx = __ldg(n4 + 0), ly = __ldg(n4 + 2), lz = __ldg(n4 + 4), hx = __ldg(n4 + 6), hy = __ldg(n4 + 8), hz = __ldg(n4 + 10);
+    r.lo.x = child_entry_any(lx.x, ly.x, lz.x, hx.x, hy.x, hz.x, ox, oy, oz, ix, iy, iz, t_max);
+    r.lo.y = child_entry_any(lx.y, ly.y, lz.y, hx.y, hy.y, hz.y, ox, oy, oz, ix, iy, iz, t_max);
+    r.lo.z = child_entry_any(lx.z, ly.z, lz.z, hx.z, hy.z, hz.z, ox, oy, oz, ix, iy, iz, t_max);
+    r.lo.w = child_entry_any(lx.w, ly.w, lz.w, hx.w, hy.w, hz.w, ox, oy, oz, ix, iy, iz, t_max);
+  }
+  {
+    float4 lx = __ldg(n4 + 1), ly = __ldg(n4 + 3), lz = __ldg(n4 + 5), hx = __ldg(n4 + 7), hy = __ldg(n4 + 9), hz = __ldg(n4 + 11);
+    r.hi.x = child_entry_any(lx.x, ly.x, lz.x, hx.x, hy.x, hz.x, ox, oy, oz, ix, iy, iz, t_max);
+    r.hi.y = child_entry_any(lx.y, ly.y, lz.y, hx.y, hy.y, hz.y, ox, oy, oz, ix, iy, iz, t_max);
+    r.hi.z = child_entry_any(lx.z, ly.z, lz.z, hx.z, hy.z, hz.z, ox, oy, oz, ix, iy, iz, t_max);
+    r.hi.w = child_entry_any(lx.w, ly.w, lz.w, hx.w, hy.w, hz.w, ox, oy, oz, ix, iy, iz, t_max);
+  }
+  return r;
 }
 
 // fminf ignores NaN operands: the minimum of the ordered entries (NaN only if all eight are NaN)
@@ -78,16 +103,16 @@ __device__ __forceinline__ float min8(const float (&e)[8]) {
 // untried candidates in shared memory, and `pending` (bit = level) lets a pop jump straight
 // to the nearest such ancestor.  Visit order and every compare are the reference's, so the
 // closest hit — ties included — is the same triangle slot.
-// Shape: while-while with explicit reconvergence, driven by the caller (rt_trace_kernel):
-//   walk_to_leaf  lanes walk internal nodes until each holds a leaf or is done   (divergent)
-//   __syncwarp
-//   walk_leaf     the warp runs the triangle loop together
+// Shape: two kinds of step, scheduled by the caller (rt_trace_kernel) by majority vote so the
+// warp always runs the step most of its lanes are waiting for:
+//   walk_node_step  box-test one node and pick its nearest untried child
+//   walk_leaf       test the eight triangles of the leaf the lane holds
 struct RayWalk {
   float ox, oy, oz, dx, dy, dz, ix, iy, iz;
   float hit_t, hit_u, hit_v;
   int   hit_slot;
   int   node, level, leaf;
-  unsigned pending;
+  unsigned pending, near_rows;
   float e[8];
   bool  need_box, regular, done;
 };
@@ -97,21 +122,27 @@ __device__ __forceinline__ void walk_begin(RayWalk &w, const SceneDev &sc, float
   w.ox = ox; w.oy = oy; w.oz = oz; w.dx = dx; w.dy = dy; w.dz = dz;
   w.ix = 1.0f / dx; w.iy = 1.0f / dy; w.iz = 1.0f / dz;                // raytracer.c:198-202
   // a zero direction component makes 1/d infinite and 0 * inf NaN: only then the slab test
-  // needs the exact MINPS/MAXPS operand-order rule (see child_entry)
+  // needs the exact MINPS/MAXPS operand-order rule (see child_entry_any)
   w.regular = (fabsf(w.ix) < CUDART_INF_F) & (fabsf(w.iy) < CUDART_INF_F) & (fabsf(w.iz) < CUDART_INF_F);
+  w.near_rows = (w.ix < 0.0f ? 1u : 0u) | (w.iy < 0.0f ? 2u : 0u) | (w.iz < 0.0f ? 4u : 0u);
   w.node = 0; w.level = sc.depth;                                       // raytracer.c:501
   w.pending = 0; w.leaf = -1;
   w.need_box = true; w.done = false;
   w.hit_t = CUDART_INF_F; w.hit_u = 0; w.hit_v = 0; w.hit_slot = -1;
 }
 
-__device__ __forceinline__ void walk_to_leaf(RayWalk &w, const SceneDev &sc, float4 *levels, unsigned &c_nodes) {
+// One node step: (box-test the node just entered,) pick the next child; ends with a leaf to test,
+// a child to enter on the next step, or the walk done.
+__device__ __forceinline__ void walk_node_step(RayWalk &w, const SceneDev &sc, float4 *levels, unsigned &c_nodes) {
   float (&e)[8] = w.e;
-  while (!w.done && w.leaf < 0) {
+  for (;;) {
     if (w.need_box) {
       const float4 *n4 = (const float4 *)(sc.nodes + (size_t)w.node * 48);
-      if (w.regular) node_entries<true >(n4, w.ox, w.oy, w.oz, w.ix, w.iy, w.iz, w.hit_t, e);
-      else           node_entries<false>(n4, w.ox, w.oy, w.oz, w.ix, w.iy, w.iz, w.hit_t, e);
+      if (w.regular) node_entries_regular(n4, w.near_rows, w.ox, w.oy, w.oz, w.ix, w.iy, w.iz, w.hit_t, e);
+      else {
+        const Entries8 r = node_entries_any(n4, w.ox, w.oy, w.oz, w.ix, w.iy, w.iz, w.hit_t);
+        e[0] = r.lo.x; e[1] = r.lo.y; e[2] = r.lo.z; e[3] = r.lo.w; e[4] = r.hi.x; e[5] = r.hi.y; e[6] = r.hi.z; e[7] = r.hi.w;
+      }
       w.need_box = false;
       c_nodes++;
     }
@@ -142,6 +173,7 @@ __device__ __forceinline__ void walk_to_leaf(RayWalk &w, const SceneDev &sc, flo
     w.node = child;
     w.level -= 1;
     w.need_box = true;
+    break;
   }
 }
 

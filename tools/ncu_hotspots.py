@@ -110,5 +110,17 @@ def main():
               f"{100 * a['samples'] / max(total_samples, 1):6.2f} {a['thr'] / max(a['inst'], 1):8.1f}  {st_s}")
 
 
+    if len(sys.argv) > 4:
+        # listing mode: every source line of the functions matching argv[4], in file order
+        pat = sys.argv[4]
+        ftot = sum(a["inst"] for k, a in agg.items() if pat in k[0])
+        print(f"\nlines of functions matching {pat!r} (inst% of that function, {ftot:,} warp-instructions):")
+        for key, a in sorted(agg.items(), key=lambda kv: (kv[0][0], kv[0][1], kv[0][2])):
+            if pat not in key[0] or a["inst"] * 500 < ftot:
+                continue
+            print(f"{key[0]:28s} {key[1] + ':' + str(key[2]):28s} {100 * a['inst'] / max(ftot, 1):6.2f} "
+                  f"{100 * a['samples'] / max(total_samples, 1):6.2f} {a['thr'] / max(a['inst'], 1):8.1f}")
+
+
 if __name__ == "__main__":
     main()
