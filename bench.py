@@ -9,8 +9,10 @@ A step = one full frame of BASELINE.json's headline config (helmet.glb, 1920x108
 pixel into an f32 accumulator (spp-range split), the accumulators are summed to rank 0
 with one NCCL reduce, rank 0 resolves to u8 sRGB.  The total work is fixed => "scaling": "strong".
 
-Keys beyond the base contract: `roofline` (the trace kernel against the measured FP32 issue
-ceiling, the bound SURVEY §8d derives — not HBM, not tensor), `cpu_baseline` (the oracle timed on
+Keys beyond the base contract: `roofline` (rt_trace_kernel — BVH traversal, the dominant kernel of
+the wavefront — against the measured FP32 issue ceiling, the bound SURVEY §8d derives: not HBM,
+not tensor; its launch time is measured live with CUDA events around every launch of the timed
+region, rt_gpu_stage_profile_*), `cpu_baseline` (the oracle timed on
 the host cores on a bounded sample), `e2e` (the same frame through the reference entry point
 render_thread_proc with HOST buffers: scene upload H2D and image D2H inside the timed region).
 """
@@ -210,27 +212,18 @@ def run_gpu(args) -> None:
     stream = torch.cuda.current_stream()
     sptr = C.c_void_p(stream.cuda_stream)
     launches = {"n": 0}
-    kernel_events = []
 
     def step(timed: bool):
         flush.zero_()                                              # L2 flush between steps
-        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        k0.record(stream)
-        a, first = s_begin, True
-        while a < s_end:
-            b = min(a + slice_spp, s_end)
-            gpu_check(gpu.rt_gpu_render_accum_device(scene_ref, W, H, a, b, B, 0, 0 if first else 1, accum.data_ptr(),
-                                                     None, None, counters.data_ptr() if timed else None, sptr))
-            launches["n"] += 1
-            a, first = b, False
-        k1.record(stream)
-        if timed:
-            kernel_events.append((k0, k1, (s_end - s_begin + slice_spp - 1) // slice_spp))
+        n0 = gpu.rt_gpu_last_launches()
+        # one call: the library cuts [s_begin, s_end) into chunks of as many samples as its path queues hold
+        gpu_check(gpu.rt_gpu_render_accum_device(scene_ref, W, H, s_begin, s_end, B, 0, 0, accum.data_ptr(),
+                                                 None, None, counters.data_ptr() if timed else None, sptr))
         if world > 1:
             dist.reduce(accum, dst=0, op=dist.ReduceOp.SUM)        # NCCL over NVLink: 24.9 MB f32
         if rank == 0:
             gpu_check(gpu.rt_gpu_resolve_device(accum.data_ptr(), W, H, SPP, pixels.data_ptr(), W, 3, sptr))
-            launches["n"] += 1
+        launches["n"] += gpu.rt_gpu_last_launches() - n0
 
     def barrier():
         if world > 1:
@@ -241,6 +234,7 @@ def run_gpu(args) -> None:
         step(False)
     barrier()
     launches["n"] = 0
+    gpu.rt_gpu_stage_profile_enable(1)
     sampler = ClockSampler(local)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -257,30 +251,41 @@ def run_gpu(args) -> None:
     ms_per_step = total_ms / args.steps
     value = W * H * SPP / (ms_per_step * 1e-3) / 1e6
 
-    # dominant kernel: rt_render_kernel, averaged over this rank's timed launches
-    kern_ms = sum(a.elapsed_time(b) for a, b, _ in kernel_events)
-    n_kern = sum(n for _, _, n in kernel_events)
+    # dominant kernel: rt_trace_kernel (closest-hit BVH traversal; primary and bounce launches are one template),
+    # CUDA-event time of every launch in the timed region on this rank
+    stage_ms, stage_n = (C.c_double * 4)(), (C.c_int64 * 4)()
+    gpu_check(gpu.rt_gpu_stage_profile_read(C.byref(stage_ms), C.byref(stage_n)))
+    gpu.rt_gpu_stage_profile_enable(0)
+    stage_names = ["trace", "miss", "shade", "accumulate"]
+    kern_ms, n_kern = float(stage_ms[0]), int(stage_n[0])
     ctr = dict(zip(COUNTER_NAMES, [int(v) for v in counters.cpu().tolist()]))
-    flops_per_launch = algorithmic_flops(ctr) / max(n_kern, 1)
+    trace_flops = (FLOP_RAYGEN * ctr["samples"] + FLOP_NODE * ctr["nodes"] + FLOP_LEAF * ctr["leaves"] +
+                   FLOP_ACCEPT * ctr["accepts"])
+    flops_per_launch = trace_flops / max(n_kern, 1)
     achieved_tflops = flops_per_launch / (kern_ms / max(n_kern, 1) * 1e-3) / 1e12
     peak_ops = float(gpu.rt_gpu_measure_fp32_issue())
     traffic = None
     prof = os.path.join(ROOT, "profiles", "dram_traffic.json")
     if os.path.exists(prof):
         try:
-            traffic = json.load(open(prof)).get("rt_render_kernel_bytes_per_launch")
+            traffic = json.load(open(prof)).get("rt_trace_kernel_bytes_per_launch")
         except Exception:
             traffic = None
-    cache_bytes = (BYTES_NODE * ctr["nodes"] + BYTES_LEAF * ctr["leaves"] + BYTES_ACCEPT * ctr["accepts"] +
-                   BYTES_SHADE * ctr["shades"]) / max(n_kern, 1)
-    roofline = {"kernel": "rt_render_kernel", "bound": "fp32_issue (not hbm, not tensor: SURVEY 8d)",
+    cache_bytes = (BYTES_NODE * ctr["nodes"] + BYTES_LEAF * ctr["leaves"] + BYTES_ACCEPT * ctr["accepts"]) / max(n_kern, 1)
+    all_ms = sum(float(v) for v in stage_ms)
+    roofline = {"kernel": "rt_trace_kernel", "bound": "fp32_issue (not hbm, not tensor: SURVEY 8d)",
                 "achieved": round(achieved_tflops, 3), "peak": round(peak_ops / 1e12, 3), "unit": "TFLOP/s",
                 "frac": round(achieved_tflops / (peak_ops / 1e12), 4) if peak_ops else None, "traffic": traffic,
                 "peak_source": "measured live: non-fused FMUL+FADD issue rate (csrc/rt_peak.cu); MEASURED_PEAKS.json has no FP32 entry",
-                "flop_model": "SURVEY 8d: 40/sample + 200/node + 456/leaf + 33/accept + 700/shade + 90/miss, from the kernel's own counters",
-                "flops_per_launch": flops_per_launch, "launch_ms": round(kern_ms / max(n_kern, 1), 4),
+                "flop_model": "SURVEY 8d, traversal terms: 40/sample ray-gen + 200/node + 456/leaf + 33/accept, from the kernels' own counters",
+                "flops_per_launch": flops_per_launch, "launch_ms": round(kern_ms / max(n_kern, 1), 4), "launches": n_kern,
                 "cache_level_bytes_per_launch": cache_bytes,
-                "hbm_compulsory_bytes_per_launch": scene_bytes + 2 * W * H * 12,
+                "hbm_compulsory_bytes_per_step": scene_bytes + 2 * W * H * 12,
+                "stage_share_of_kernel_time": {k: round(float(stage_ms[i]) / all_ms, 4) if all_ms else None
+                                               for i, k in enumerate(stage_names)},
+                "stage_launches": {k: int(stage_n[i]) for i, k in enumerate(stage_names)},
+                "whole_step": {"flops": algorithmic_flops(ctr) / args.steps, "kernel_ms": round(all_ms / args.steps, 3),
+                               "achieved_tflops": round(algorithmic_flops(ctr) / (all_ms * 1e-3) / 1e12, 3) if all_ms else None},
                 "per_sample": {k: round(ctr[k] / max(ctr["samples"], 1), 3) for k in ("rays", "nodes", "leaves", "shades", "misses")}}
 
     # ---- e2e: through render_thread_proc with HOST buffers (N=1), or its device-level pieces + NCCL (N>1)
@@ -322,7 +327,7 @@ def run_gpu(args) -> None:
                 "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": dict(workload_config(args, f"spp-range split x{world}, NCCL reduce(sum) of the f32 accumulator to rank 0"),
                                l2="flushed between steps (256 MiB memset inside the timed region, ~0.05 ms)",
-                               slice_spp=slice_spp),
+                               chunk="the library renders as many samples of every pixel per wavefront chunk as its 32 Mi-path queues hold"),
                 "clocks": clocks, "gpu_launches": launches["n"],
                 "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": scene_bytes,
                         "d2h_bytes_per_step": W * H * 3,
@@ -347,7 +352,7 @@ def main() -> None:
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--spp", type=int, default=1024)
     ap.add_argument("--bounces", type=int, default=8)
-    ap.add_argument("--slice", type=int, default=32, help="samples per kernel launch")
+    ap.add_argument("--slice", type=int, default=64, help="e2e leg: samples per progress slice of render_thread_proc")
     ap.add_argument("--cpu-spp", type=int, default=4, help="--impl reference: spp of each bounded CPU step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()

@@ -21,6 +21,7 @@ extern "C" {
 typedef float     f32;
 typedef double    f64;
 typedef int32_t   i32;
+typedef int64_t   i64;
 typedef uint32_t  u32;
 typedef uint64_t  u64;
 typedef uint8_t   u8;

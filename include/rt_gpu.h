@@ -64,8 +64,14 @@ enum {
 int rt_gpu_read_accum(f32 *out, isize n_floats);       /* W*H*3 sums of cast_ray, pre-division */
 int rt_gpu_read_hit_ids(i32 *out, isize n_pixels);     /* padded slot or -1 */
 int rt_gpu_read_counters(u64 out[8]);
-int rt_gpu_last_launches(void);                        /* kernels launched by the last entry-point call */
+int rt_gpu_last_launches(void);                        /* kernels launched since the last entry-point call began */
 f64 rt_gpu_last_kernel_ms(void);                       /* CUDA-event time of the last call's trace kernels */
+
+/* ---- per-stage kernel timing (measurement harness): when enabled, every kernel of a render is
+ *      bracketed by CUDA events on its launching stream; read = synchronise + sum since enable.
+ *      Stages: 0 trace (closest hit), 1 miss (environment), 2 shade (BSDF), 3 accumulate. ---- */
+void rt_gpu_stage_profile_enable(i32 on);
+int  rt_gpu_stage_profile_read(f64 ms[4], i64 launches[4]);
 
 /* ---- device-pointer level (all pointers are device memory; stream is a
  *      cudaStream_t passed as void*, NULL = the legacy default stream) ---- */

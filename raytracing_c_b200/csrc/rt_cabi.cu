@@ -441,6 +441,20 @@ int rt_gpu_read_counters(u64 out[8]) {
 }
 
 int rt_gpu_last_launches(void) { return g.last_launches; }
+
+void rt_gpu_stage_profile_enable(i32 on) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  rt_stage_profile_enable(on);
+}
+
+int rt_gpu_stage_profile_read(f64 ms[4], i64 launches[4]) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  long long n[RT_N_STAGES];
+  int e = rt_stage_profile_read(ms, n);
+  if (e) return fail("stage profile: %s", cudaGetErrorString((cudaError_t)e));
+  for (int i = 0; i < RT_N_STAGES; i++) launches[i] = n[i];
+  return 0;
+}
 f64 rt_gpu_last_kernel_ms(void) { return g.last_kernel_ms; }
 
 // ------------------------------------------------------- reference entry points

@@ -35,9 +35,6 @@
 #ifndef RT_TRACE_MIN_BLOCKS
 #define RT_TRACE_MIN_BLOCKS 3
 #endif
-#ifndef RT_TRACE_LANE_BLOCKS
-#define RT_TRACE_LANE_BLOCKS 2
-#endif
 #define RT_FULL 0xffffffffu
 
 // counts[bounce][...]: queue lengths written by one stage and read by the next
@@ -416,10 +413,50 @@ size_t rt_render_workspace_bytes(int width, int height, int n_samples, int max_b
 
 static int g_trace_blocks_per_sm = 0;
 static size_t g_level_bytes = 0;
-// Two chunks are kept in flight on two helper streams: the low-occupancy tail of one chunk
-// (late bounces hold few rays) overlaps the full-width kernels of the next.
-static cudaStream_t g_lane_stream[2] = { nullptr, nullptr };
-static cudaEvent_t  g_ev_fork = nullptr, g_ev_chunk[2] = { nullptr, nullptr }, g_ev_acc[2] = { nullptr, nullptr };
+
+// ---- optional per-stage timing (bench.py's roofline leg): CUDA events around every launch, on the
+// launching stream; read back and summed by rt_stage_profile_read
+#include <vector>
+struct StageEvent { cudaEvent_t a, b; int stage; };
+static bool g_profile = false;
+static std::vector<StageEvent> g_stage_events;
+static std::vector<cudaEvent_t> g_event_pool;
+
+static cudaEvent_t pooled_event() {
+  if (!g_event_pool.empty()) { cudaEvent_t e = g_event_pool.back(); g_event_pool.pop_back(); return e; }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+
+struct StageTimer {
+  cudaStream_t st; bool on; StageEvent ev;
+  StageTimer(int stage, cudaStream_t s) : st(s), on(g_profile) {
+    if (on) { ev.a = pooled_event(); ev.b = pooled_event(); ev.stage = stage; cudaEventRecord(ev.a, st); }
+  }
+  ~StageTimer() { if (on) { cudaEventRecord(ev.b, st); g_stage_events.push_back(ev); } }
+};
+
+void rt_stage_profile_enable(int on) {
+  g_profile = on != 0;
+  for (StageEvent &e : g_stage_events) { g_event_pool.push_back(e.a); g_event_pool.push_back(e.b); }
+  g_stage_events.clear();
+}
+
+int rt_stage_profile_read(double ms[RT_N_STAGES], long long launches[RT_N_STAGES]) {
+  for (int i = 0; i < RT_N_STAGES; i++) { ms[i] = 0; launches[i] = 0; }
+  for (StageEvent &e : g_stage_events) {
+    cudaError_t err = cudaEventSynchronize(e.b);
+    if (err != cudaSuccess) return (int)err;
+    float t = 0;
+    cudaEventElapsedTime(&t, e.a, e.b);
+    ms[e.stage] += t;
+    launches[e.stage] += 1;
+    g_event_pool.push_back(e.a); g_event_pool.push_back(e.b);
+  }
+  g_stage_events.clear();
+  return 0;
+}
 
 static void bind_queues(PathQueues &q, char *w, size_t cb, size_t cap) {
   q.counts = reinterpret_cast<unsigned *>(w); w += cb;
@@ -446,14 +483,6 @@ int rt_launch_render(const RenderParams &p, int sm_count, void *workspace, size_
     g_trace_blocks_per_sm = n;
     g_level_bytes = level_bytes;
   }
-  if (!g_ev_fork) {
-    for (int i = 0; i < 2; i++) {
-      if (cudaStreamCreateWithFlags(&g_lane_stream[i], cudaStreamNonBlocking) != cudaSuccess) return (int)cudaGetLastError();
-      cudaEventCreateWithFlags(&g_ev_chunk[i], cudaEventDisableTiming);
-      cudaEventCreateWithFlags(&g_ev_acc[i], cudaEventDisableTiming);
-    }
-    cudaEventCreateWithFlags(&g_ev_fork, cudaEventDisableTiming);
-  }
 
   StageParams P{};
   P.scene = p.scene;
@@ -466,60 +495,42 @@ int rt_launch_render(const RenderParams &p, int sm_count, void *workspace, size_
   P.per_sample_stride = n_total;
   P.counters = p.counters;
 
-  // chunking: the workspace is one set of queues when the whole job fits in it, else two halves
+  // chunking: as many samples of every pixel per chunk as the workspace holds paths
   const size_t per_sample = (size_t)P.tiles_x * (size_t)P.tiles_y * 32;
   const size_t cb = counts_bytes(p.max_bounces);
   if (workspace_bytes < cb + per_sample * RT_PATH_BYTES) return (int)cudaErrorMemoryAllocation;
-  const size_t half_bytes = (workspace_bytes / 2) & ~(size_t)255;
-  int    lanes = 1;
-  size_t cap = (workspace_bytes - cb) / RT_PATH_BYTES;             // paths one set of queues holds
-  if (cap / per_sample < (size_t)n_total && half_bytes >= cb + per_sample * RT_PATH_BYTES) {
-    lanes = 2;
-    cap = (half_bytes - cb) / RT_PATH_BYTES;
-  }
+  size_t cap = (workspace_bytes - cb) / RT_PATH_BYTES;
   const int chunk = (int)(cap / per_sample < (size_t)n_total ? cap / per_sample : (size_t)n_total);
   cap = (size_t)chunk * per_sample;
-  PathQueues queues[2];
-  for (int i = 0; i < lanes; i++) bind_queues(queues[i], static_cast<char *>(workspace) + (size_t)i * half_bytes, cb, cap);
+  bind_queues(P.q, static_cast<char *>(workspace), cb, cap);
 
-  // persistent trace grids: with two chunks in flight each takes 2 of the (usually 3) block slots of an SM,
-  // so a kernel of the other chunk always finds room instead of queueing behind a full machine
-  int per_sm = g_trace_blocks_per_sm;
-  if (lanes == 2 && per_sm > RT_TRACE_LANE_BLOCKS) per_sm = RT_TRACE_LANE_BLOCKS;
-  const unsigned trace_grid = (unsigned)(sm_count * per_sm);
+  const unsigned trace_grid = (unsigned)(sm_count * g_trace_blocks_per_sm);     // persistent: one wave
   const unsigned flat_grid  = (unsigned)(sm_count * 8);
-  int launches = 0, k = 0;
-  cudaEventRecord(g_ev_fork, stream);
-  for (int s0 = p.sample_begin; s0 < p.sample_end; s0 += chunk, k++) {
-    const int lane = k % lanes;
-    cudaStream_t st = g_lane_stream[lane];
-    // this lane's queues are free once the accumulate of the chunk that used them last has run
-    cudaStreamWaitEvent(st, k < lanes ? g_ev_fork : g_ev_acc[lane], 0);
-
+  int launches = 0;
+  for (int s0 = p.sample_begin; s0 < p.sample_end; s0 += chunk) {
     const int S = (p.sample_end - s0 < chunk) ? p.sample_end - s0 : chunk;
-    P.q = queues[lane];
     P.sample0 = s0; P.n_samples = S;
     P.n_paths = (unsigned)(per_sample * (size_t)S);
     P.accumulate = (p.accumulate || s0 > p.sample_begin) ? 1 : 0;
     P.per_sample_offset = s0 - p.sample_begin;
     P.hit_ids = (s0 == p.sample_begin) ? p.hit_ids : nullptr;
-    cudaMemsetAsync(P.q.counts, 0, cb, st);
+    cudaMemsetAsync(P.q.counts, 0, cb, stream);
     P.bounce = 0;
-    rt_trace_kernel<true><<<trace_grid, RT_BLOCK, level_bytes, st>>>(P);
+    { StageTimer t(RT_STAGE_TRACE, stream); rt_trace_kernel<true><<<trace_grid, RT_BLOCK, level_bytes, stream>>>(P); }
     launches++;
     for (int b = 0; b < p.max_bounces; b++) {
       P.bounce = b;
-      if (b > 0) { rt_trace_kernel<false><<<trace_grid, RT_BLOCK, level_bytes, st>>>(P); launches++; }
-      rt_miss_kernel<<<flat_grid, 256, 0, st>>>(P);
-      rt_shade_kernel<<<flat_grid, 256, 0, st>>>(P);
+      if (b > 0) {
+        StageTimer t(RT_STAGE_TRACE, stream);
+        rt_trace_kernel<false><<<trace_grid, RT_BLOCK, level_bytes, stream>>>(P);
+        launches++;
+      }
+      { StageTimer t(RT_STAGE_MISS, stream);  rt_miss_kernel<<<flat_grid, 256, 0, stream>>>(P); }
+      { StageTimer t(RT_STAGE_SHADE, stream); rt_shade_kernel<<<flat_grid, 256, 0, stream>>>(P); }
       launches += 2;
     }
-    // the per-pixel sums run on the caller's stream, one chunk after the other, in sample order
-    cudaEventRecord(g_ev_chunk[lane], st);
-    cudaStreamWaitEvent(stream, g_ev_chunk[lane], 0);
-    rt_accumulate_kernel<<<flat_grid, 256, 0, stream>>>(P);
+    { StageTimer t(RT_STAGE_ACCUMULATE, stream); rt_accumulate_kernel<<<flat_grid, 256, 0, stream>>>(P); }
     launches++;
-    cudaEventRecord(g_ev_acc[lane], stream);
   }
   if (n_launches) *n_launches += launches;
   return (int)cudaGetLastError();
