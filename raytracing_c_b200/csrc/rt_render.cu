@@ -27,6 +27,9 @@
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
+#include <cstdlib>
+#include <vector>
+
 #include "rt_device.cuh"
 #include "rt_trace.cuh"
 #include "rt_shade.cuh"
@@ -402,13 +405,29 @@ static size_t counts_bytes(int max_bounces) {
   return (b + 255) & ~(size_t)255;
 }
 
-size_t rt_render_workspace_bytes(int width, int height, int n_samples, int max_bounces, int slice_samples) {
-  const size_t per_sample = (size_t)((width + 7) / 8) * (size_t)((height + 3) / 4) * 32;
-  size_t s = RT_CHUNK_PATHS_MAX / per_sample;
+// Paths per wavefront chunk: enough to fill the machine many times over, small enough that the
+// queues (208 B per path) stay a few GB.  RT_GPU_CHUNK_PATHS overrides it (tuning / tests).
+static size_t chunk_paths_max() {
+  if (const char *e = getenv("RT_GPU_CHUNK_PATHS")) {
+    unsigned long long v = strtoull(e, nullptr, 10);
+    if (v > 0) return (size_t)v;
+  }
+  return RT_CHUNK_PATHS_MAX;
+}
+
+// samples of every pixel per chunk
+static size_t chunk_samples(size_t per_sample, int n_samples, int slice_samples) {
+  size_t s = chunk_paths_max() / per_sample;
   if (s < 1) s = 1;
   if (slice_samples > 0 && s > (size_t)slice_samples) s = (size_t)slice_samples;
   if (n_samples > 0 && s > (size_t)n_samples) s = (size_t)n_samples;
-  return counts_bytes(max_bounces > 0 ? max_bounces : 1) + s * per_sample * RT_PATH_BYTES;
+  return s;
+}
+
+size_t rt_render_workspace_bytes(int width, int height, int n_samples, int max_bounces, int slice_samples) {
+  const size_t per_sample = (size_t)((width + 7) / 8) * (size_t)((height + 3) / 4) * 32;
+  return counts_bytes(max_bounces > 0 ? max_bounces : 1) +
+         chunk_samples(per_sample, n_samples, slice_samples) * per_sample * RT_PATH_BYTES;
 }
 
 static int g_trace_blocks_per_sm = 0;
@@ -416,7 +435,6 @@ static size_t g_level_bytes = 0;
 
 // ---- optional per-stage timing (bench.py's roofline leg): CUDA events around every launch, on the
 // launching stream; read back and summed by rt_stage_profile_read
-#include <vector>
 struct StageEvent { cudaEvent_t a, b; int stage; };
 static bool g_profile = false;
 static std::vector<StageEvent> g_stage_events;
@@ -500,7 +518,9 @@ int rt_launch_render(const RenderParams &p, int sm_count, void *workspace, size_
   const size_t cb = counts_bytes(p.max_bounces);
   if (workspace_bytes < cb + per_sample * RT_PATH_BYTES) return (int)cudaErrorMemoryAllocation;
   size_t cap = (workspace_bytes - cb) / RT_PATH_BYTES;
-  const int chunk = (int)(cap / per_sample < (size_t)n_total ? cap / per_sample : (size_t)n_total);
+  size_t fit = chunk_samples(per_sample, n_total, 0);
+  if (fit > cap / per_sample) fit = cap / per_sample;
+  const int chunk = (int)fit;
   cap = (size_t)chunk * per_sample;
   bind_queues(P.q, static_cast<char *>(workspace), cb, cap);
 

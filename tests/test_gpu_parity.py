@@ -187,6 +187,46 @@ def test_max_bounces_and_seed():
         loaded.close()
 
 
+def test_converged_image_rmse_with_independent_seeds():
+    """North star: converged images within a stated RMSE.  Stated here: at 1024 spp with
+    INDEPENDENT seeds on the two sides, sRGB u8/255 RMSE <= 0.01 and mean luminance within 0.5 %."""
+    loaded = load("spheres.glb")
+    try:
+        w, h, spp = 160, 90, 1024
+        got = gpu_render(loaded, w, h, spp, user_seed=1)
+        ref = oracle_ffi.render(loaded, w, h, spp, n_threads=8, user_seed=2)
+        a, b = got["pixels"].astype(np.float64) / 255.0, ref["pixels"].astype(np.float64) / 255.0
+        rmse = float(np.sqrt(np.mean((a - b) ** 2)))
+        assert rmse <= 0.01, f"converged-image RMSE {rmse}"
+        lum = np.array([0.2126, 0.7152, 0.0722])
+        ratio = float((got["accum"].astype(np.float64) @ lum).mean() / (ref["accum"].astype(np.float64) @ lum).mean())
+        assert abs(ratio - 1.0) <= 0.005, f"mean luminance ratio {ratio}"
+    finally:
+        loaded.close()
+
+
+def test_wavefront_chunking_is_invisible(monkeypatch):
+    """The path queues hold a bounded number of paths (RT_GPU_CHUNK_PATHS); however one render call is
+    cut into chunks (1, 3 or all 7 samples per chunk here) the f32 accumulator, hit ids and counters
+    are identical — and equal to the oracle's."""
+    loaded = load("helmet.glb")
+    try:
+        w, h, spp = 120, 68, 7
+        per_sample = ((w + 7) // 8) * ((h + 3) // 4) * 32
+        base = gpu_render(loaded, w, h, spp, slice_samples=spp)
+        ref = oracle_ffi.render(loaded, w, h, spp, n_threads=8, want_hit_ids=True)
+        assert np.array_equal(base["accum"], ref["accum"])
+        for per_chunk in (1, 3):
+            monkeypatch.setenv("RT_GPU_CHUNK_PATHS", str(per_sample * per_chunk))
+            other = gpu_render(loaded, w, h, spp, slice_samples=spp)
+            assert gpu_lib().rt_gpu_last_launches() >= 25 * -(-spp // per_chunk)      # 25 kernels per chunk at 8 bounces
+            assert np.array_equal(base["accum"], other["accum"])
+            assert np.array_equal(base["hit_ids"], other["hit_ids"])
+            assert base["counters"] == other["counters"]
+    finally:
+        loaded.close()
+
+
 def test_unregistered_shader_is_an_error():
     loaded = driver.load_scene(os.path.join(MODELS, "quad.obj"), shader_proc=0xDEAD0, background_proc=oracle_ffi.background_proc())
     try:
