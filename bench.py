@@ -204,6 +204,7 @@ def run_gpu(args) -> None:
     torch.cuda.synchronize()
     t_upload = time.perf_counter() - t0
     scene_bytes = int(gpu.rt_gpu_scene_device_bytes(scene_ref))
+    upload_bytes = int(gpu.rt_gpu_scene_upload_bytes(scene_ref))
 
     accum = torch.zeros(H * W * 3, dtype=torch.float32, device=dev)
     pixels = torch.zeros(H * W * 3, dtype=torch.uint8, device=dev)
@@ -244,6 +245,7 @@ def run_gpu(args) -> None:
     e1.record(stream)
     barrier()
     clocks = sampler.finish()
+    timed_launches = launches["n"]
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -328,8 +330,8 @@ def run_gpu(args) -> None:
                 "config": dict(workload_config(args, f"spp-range split x{world}, NCCL reduce(sum) of the f32 accumulator to rank 0"),
                                l2="flushed between steps (256 MiB memset inside the timed region, ~0.05 ms)",
                                chunk="the library renders as many samples of every pixel per wavefront chunk as its 32 Mi-path queues hold"),
-                "clocks": clocks, "gpu_launches": launches["n"],
-                "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": scene_bytes,
+                "clocks": clocks, "gpu_launches": timed_launches,
+                "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": upload_bytes,
                         "d2h_bytes_per_step": W * H * 3,
                         "how": "rt_gpu_scene_upload + render_thread_proc(host Image) per step" if world == 1 else
                                "scene upload + per-rank render + NCCL reduce + resolve + D2H to pinned host on rank 0"},

@@ -43,6 +43,7 @@ Color3 rt_gpu_background_proc(rawptr image, Vec3 direction);
 /* ---- scene residency: upload once, keyed by the Scene pointer ---- */
 int  rt_gpu_scene_upload(Scene const *scene);
 isize rt_gpu_scene_device_bytes(Scene const *scene);   /* bytes resident for this scene, 0 if absent */
+isize rt_gpu_scene_upload_bytes(Scene const *scene);   /* bytes its upload copied host -> device */
 void rt_gpu_scene_release(Scene const *scene);
 
 /* ---- options for the raytracer.h entry points ---- */

@@ -104,7 +104,7 @@ GPU_EXPORTS = [
     "denoise_image",
     # rt_gpu.h
     "rt_gpu_init", "rt_gpu_shutdown", "rt_gpu_last_error", "rt_gpu_sm_count", "rt_gpu_measure_fp32_issue",
-    "rt_gpu_scene_device_bytes",
+    "rt_gpu_scene_device_bytes", "rt_gpu_scene_upload_bytes",
     "rt_gpu_register_pbr_shader", "rt_gpu_register_background", "rt_gpu_pbr_shader_proc", "rt_gpu_background_proc",
     "rt_gpu_scene_upload", "rt_gpu_scene_release", "rt_gpu_set_options", "rt_gpu_get_options",
     "rt_gpu_read_accum", "rt_gpu_read_hit_ids", "rt_gpu_read_counters", "rt_gpu_last_launches",
@@ -173,6 +173,8 @@ def gpu_lib() -> C.CDLL:
         lib.rt_gpu_measure_fp32_issue.restype = C.c_double
         lib.rt_gpu_scene_device_bytes.restype = isize
         lib.rt_gpu_scene_device_bytes.argtypes = [C.POINTER(Scene)]
+        lib.rt_gpu_scene_upload_bytes.restype = isize
+        lib.rt_gpu_scene_upload_bytes.argtypes = [C.POINTER(Scene)]
         lib.rt_gpu_register_pbr_shader.argtypes = [C.c_void_p]
         lib.rt_gpu_register_background.argtypes = [C.c_void_p]
         lib.rt_gpu_scene_upload.argtypes = [C.POINTER(Scene)]

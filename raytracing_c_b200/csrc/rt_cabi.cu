@@ -48,8 +48,9 @@ int fail(const char *fmt, ...) {
 
 struct DeviceScene {
   SceneDev dev{};
-  std::vector<void *> allocations;
-  size_t bytes = 0;
+  std::vector<std::pair<void *, size_t>> allocations;
+  size_t bytes = 0;        // resident on the device
+  size_t h2d_bytes = 0;    // copied host -> device by the upload
 };
 
 struct State {
@@ -66,6 +67,7 @@ struct State {
   float *d_accum = nullptr;   size_t accum_floats = 0;
   int   *d_hit_ids = nullptr; size_t hit_pixels = 0;
   unsigned long long *d_counters = nullptr;
+  void  *d_texel_stage = nullptr; size_t texel_stage_bytes = 0;  // raw texture bytes before the RGBA8 repack
   void  *d_workspace = nullptr; size_t workspace_bytes = 0;     // wavefront path queues (rt_render.cu)
   unsigned char *d_image = nullptr, *d_image2 = nullptr; size_t image_bytes = 0, image2_bytes = 0;
   unsigned char *h_pinned = nullptr; size_t pinned_bytes = 0;
@@ -80,21 +82,55 @@ int ensure_init() {
   return rt_gpu_init(g.device < 0 ? 0 : g.device);
 }
 
+// Device blocks of released scenes are kept and handed out again by exact size: re-uploading a
+// scene (per frame in an interactive host, per step in bench.py's end-to-end leg) then costs no
+// cudaMalloc / cudaFree (each a device-wide synchronisation).
+std::multimap<size_t, void *> g_block_pool;
+
+int pool_alloc(void **out, size_t bytes) {
+  auto it = g_block_pool.find(bytes);
+  if (it != g_block_pool.end()) { *out = it->second; g_block_pool.erase(it); return 0; }
+  CUDA_TRY(cudaMalloc(out, bytes));
+  return 0;
+}
+
+int grow_pinned(size_t want);
+
+// host -> device through the pinned staging buffer, asynchronously on the library's stream;
+// staging is reused, so the copy of one buffer is drained before the next one is staged
+int upload_bytes(DeviceScene &ds, const void *host, size_t n, const void **out) {
+  void *p = nullptr;
+  const size_t alloc = n ? n : 16;
+  if (pool_alloc(&p, alloc)) return 1;
+  ds.allocations.push_back({p, alloc});
+  ds.bytes += n;
+  if (n) {
+    if (grow_pinned(n)) return 1;
+    CUDA_TRY(cudaStreamSynchronize(g.stream));
+    memcpy(g.h_pinned, host, n);
+    ds.h2d_bytes += n;
+    CUDA_TRY(cudaMemcpyAsync(p, g.h_pinned, n, cudaMemcpyHostToDevice, g.stream));
+  }
+  *out = p;
+  return 0;
+}
+
 template <typename T>
 int upload(DeviceScene &ds, const std::vector<T> &host, const T **out) {
-  void *p = nullptr;
-  size_t n = host.size() * sizeof(T);
-  CUDA_TRY(cudaMalloc(&p, n ? n : sizeof(T)));
-  ds.allocations.push_back(p);
-  ds.bytes += n;
-  if (n) CUDA_TRY(cudaMemcpy(p, host.data(), n, cudaMemcpyHostToDevice));
+  const void *p = nullptr;
+  if (upload_bytes(ds, host.data(), host.size() * sizeof(T), &p)) return 1;
   *out = static_cast<const T *>(p);
   return 0;
 }
 
 void release(DeviceScene &ds) {
-  for (void *p : ds.allocations) cudaFree(p);
+  for (auto &a : ds.allocations) g_block_pool.emplace(a.second, a.first);
   ds.allocations.clear();
+}
+
+void drop_block_pool() {
+  for (auto &kv : g_block_pool) cudaFree(kv.second);
+  g_block_pool.clear();
 }
 
 int grow(void **ptr, size_t *have, size_t want) {
@@ -207,14 +243,26 @@ int build_device_scene(const Scene *scene, DeviceScene &ds) {
   for (size_t i = 0; i < images.size(); i++) {
     const Image *im = images[i];
     if (im->components < 3 || !im->pixels.data) return fail("scene: texture %zu needs >= 3 u8 components", i);
-    std::vector<uchar4> rgba((size_t)im->width * (size_t)im->height);
-    for (isize y = 0; y < im->height; y++)
-      for (isize x = 0; x < im->width; x++) {
-        const u8 *p = im->pixels.data + (size_t)im->components * (size_t)(x + im->stride * y);
-        rgba[(size_t)x + (size_t)im->width * (size_t)y] = make_uchar4(p[0], p[1], p[2], 255);
-      }
-    const uchar4 *d_texels = nullptr;
-    if (upload(ds, rgba, &d_texels)) return 1;
+    // raw texel bytes go up as they are (3 B per texel for RGB8); the RGBA8 repack the samplers read
+    // (one 32-bit load per tap) is done by a kernel on the device
+    const size_t n_texels = (size_t)im->width * (size_t)im->height;
+    const size_t raw_bytes = (size_t)im->stride * (size_t)im->height * (size_t)im->components;
+    void *d_texels_raw = nullptr;
+    if (pool_alloc(&d_texels_raw, n_texels * sizeof(uchar4))) return 1;
+    ds.allocations.push_back({d_texels_raw, n_texels * sizeof(uchar4)});
+    ds.bytes += n_texels * sizeof(uchar4);
+    size_t have = g.texel_stage_bytes;
+    if (grow(&g.d_texel_stage, &have, raw_bytes)) return 1;
+    g.texel_stage_bytes = have;
+    if (grow_pinned(raw_bytes)) return 1;
+    CUDA_TRY(cudaStreamSynchronize(g.stream));
+    memcpy(g.h_pinned, im->pixels.data, raw_bytes);
+    ds.h2d_bytes += raw_bytes;
+    CUDA_TRY(cudaMemcpyAsync(g.d_texel_stage, g.h_pinned, raw_bytes, cudaMemcpyHostToDevice, g.stream));
+    int e = rt_launch_texel_repack(static_cast<const unsigned char *>(g.d_texel_stage), (int)im->width, (int)im->height,
+                                   (int)im->stride, im->components, static_cast<uchar4 *>(d_texels_raw), g.stream);
+    if (e) return fail("texel repack launch failed: %s", cudaGetErrorString((cudaError_t)e));
+    const uchar4 *d_texels = static_cast<const uchar4 *>(d_texels_raw);
     textures[i].texels = d_texels;
     textures[i].width = (int)im->width;
     textures[i].height = (int)im->height;
@@ -230,6 +278,8 @@ int build_device_scene(const Scene *scene, DeviceScene &ds) {
   dev.depth = (int)depth;
   dev.n_internal = (int)n_nodes;
   dev.n_slots = (int)n_slots;
+  // renders may run on another stream (device-pointer level): the scene is complete when this returns
+  CUDA_TRY(cudaStreamSynchronize(g.stream));
   return 0;
 }
 
@@ -304,7 +354,8 @@ void rt_gpu_shutdown(void) {
   std::lock_guard<std::mutex> lock(g_mutex);
   for (auto &kv : g.scenes) release(kv.second);
   g.scenes.clear();
-  cudaFree(g.d_accum); cudaFree(g.d_hit_ids); cudaFree(g.d_counters); cudaFree(g.d_workspace);
+  cudaFree(g.d_accum); cudaFree(g.d_hit_ids); cudaFree(g.d_counters); cudaFree(g.d_workspace); cudaFree(g.d_texel_stage);
+  drop_block_pool();
   cudaFree(g.d_image); cudaFree(g.d_image2);
   if (g.h_pinned) cudaFreeHost(g.h_pinned);
   if (g.ev0) cudaEventDestroy(g.ev0);
@@ -333,6 +384,12 @@ isize rt_gpu_scene_device_bytes(Scene const *scene) {
   return it == g.scenes.end() ? 0 : (isize)it->second.bytes;
 }
 
+isize rt_gpu_scene_upload_bytes(Scene const *scene) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  auto it = g.scenes.find(scene);
+  return it == g.scenes.end() ? 0 : (isize)it->second.h2d_bytes;
+}
+
 void rt_gpu_register_pbr_shader(Shader_Proc proc) {
   std::lock_guard<std::mutex> lock(g_mutex);
   for (Shader_Proc p : g.pbr_procs) if (p == proc) return;
@@ -359,7 +416,11 @@ int rt_gpu_scene_upload(Scene const *scene) {
   if (ensure_init()) return 1;
   std::lock_guard<std::mutex> lock(g_mutex);
   auto it = g.scenes.find(scene);
-  if (it != g.scenes.end()) { release(it->second); g.scenes.erase(it); }
+  if (it != g.scenes.end()) {
+    cudaDeviceSynchronize();          // its blocks are reused below: no render may still read them
+    release(it->second);
+    g.scenes.erase(it);
+  }
   SceneDev dev;
   return scene_on_device(scene, &dev);
 }

@@ -81,3 +81,26 @@ int rt_launch_denoise(const unsigned char *src, unsigned char *dst, int width, i
   rt_denoise_kernel<<<grid, block, 0, stream>>>(src, dst, width, height, src_stride, dst_stride, components);
   return (int)cudaGetLastError();
 }
+
+// ---------------------------------------------------------------- texel repack
+// Scene upload helper: the samplers read one 32-bit RGBA8 texel per tap (rt_shade.cuh); host
+// images are RGB8 (or RGBA8) rows with a pixel stride.
+__global__ void rt_texel_repack_kernel(const unsigned char *__restrict__ src, int width, int height, int stride,
+                                       int components, uchar4 *__restrict__ dst) {
+  const size_t n = (size_t)width * (size_t)height;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t x = i % (size_t)width, y = i / (size_t)width;
+    const unsigned char *p = src + (size_t)components * (x + (size_t)stride * y);
+    dst[i] = make_uchar4(p[0], p[1], p[2], 255);
+  }
+}
+
+int rt_launch_texel_repack(const unsigned char *src, int width, int height, int stride, int components,
+                           uchar4 *dst, cudaStream_t stream) {
+  const size_t n = (size_t)width * (size_t)height;
+  unsigned grid = (unsigned)((n + 255) / 256);
+  if (grid > 148u * 16u) grid = 148u * 16u;
+  if (grid < 1) grid = 1;
+  rt_texel_repack_kernel<<<grid, 256, 0, stream>>>(src, width, height, stride, components, dst);
+  return (int)cudaGetLastError();
+}

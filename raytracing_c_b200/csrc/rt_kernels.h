@@ -15,6 +15,9 @@ int rt_launch_resolve(const float *accum, int width, int height, int samples, un
 int rt_launch_denoise(const unsigned char *src, unsigned char *dst, int width, int height,
                       int src_stride, int dst_stride, int components, cudaStream_t stream);
 int rt_render_blocks_per_sm(void);
+// RGB8 / RGBA8 rows (stride in pixels) -> tightly packed RGBA8 texels
+int rt_launch_texel_repack(const unsigned char *src, int width, int height, int stride, int components,
+                           uchar4 *dst, cudaStream_t stream);
 // per-stage CUDA-event timing of rt_launch_render's kernels (off by default)
 enum { RT_STAGE_TRACE = 0, RT_STAGE_MISS, RT_STAGE_SHADE, RT_STAGE_ACCUMULATE, RT_N_STAGES };
 void rt_stage_profile_enable(int on);
