@@ -16,6 +16,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <cmath>
 #include <map>
 #include <mutex>
 #include <vector>
@@ -278,6 +279,19 @@ int build_device_scene(const Scene *scene, DeviceScene &ds) {
   dev.depth = (int)depth;
   dev.n_internal = (int)n_nodes;
   dev.n_slots = (int)n_slots;
+  // union of the root's child boxes; all-zero padding slots (lo == hi) can never be entered
+  // (enter >= leave) and are left out
+  for (int a = 0; a < 3; a++) { dev.root_lo[a] = INFINITY; dev.root_hi[a] = -INFINITY; }
+  for (int j = 0; j < 8; j++) {
+    const float *n0 = nodes.data();
+    bool empty = true;
+    for (int a = 0; a < 3; a++) empty &= (n0[a * 8 + j] == n0[(3 + a) * 8 + j]);
+    if (empty) continue;
+    for (int a = 0; a < 3; a++) {
+      dev.root_lo[a] = fminf(dev.root_lo[a], n0[a * 8 + j]);
+      dev.root_hi[a] = fmaxf(dev.root_hi[a], n0[(3 + a) * 8 + j]);
+    }
+  }
   // renders may run on another stream (device-pointer level): the scene is complete when this returns
   CUDA_TRY(cudaStreamSynchronize(g.stream));
   return 0;

@@ -132,7 +132,11 @@ rt_trace_kernel(const __grid_constant__ StageParams P) {
   RayWalk w;
   w.done = true; w.leaf = -1;
   bool     has_ray = false, exhausted = false;
-  unsigned q = 0;
+  unsigned q = 0, range_next = 0, range_end = 0;
+  // rays reserved per atomic: large queues amortise the round trip, small ones (late bounces)
+  // spread over all warps of the grid
+  const unsigned total_warps = gridDim.x * (RT_BLOCK / 32);
+  const unsigned batch = min(256u, max(32u, (n_in / (total_warps * 4u)) & ~31u));
 
   for (;;) {
     const unsigned walking = __ballot_sync(RT_FULL, has_ray && !w.done);
@@ -176,22 +180,28 @@ rt_trace_kernel(const __grid_constant__ StageParams P) {
         }
         if (is_hit | is_miss) has_ray = false;
       }
-      // ---- refill: every lane that is not walking takes the next ray of the queue
+      // ---- refill: lanes that are not walking take the next rays of the warp's reserved range;
+      // a warp reserves `batch` consecutive rays per atomic (one round trip per batch, not per refill)
       if (!exhausted) {
         const unsigned idle = ~walking;
-        const unsigned need = (unsigned)__popc(idle);
-        unsigned base = 0;
-        if (lane == 0) base = atomicAdd(&counts[Q_FETCH], need);
-        base = __shfl_sync(RT_FULL, base, 0);
-        exhausted = base + need >= n_in;
-        if (idle >> lane & 1u) {
-          q = base + (unsigned)__popc(idle & lt_mask);
-          bool ok = q < n_in;
+        if (range_next >= range_end) {
+          unsigned base = 0;
+          if (lane == 0) base = atomicAdd(&counts[Q_FETCH], batch);
+          base = __shfl_sync(RT_FULL, base, 0);
+          exhausted = base >= n_in;
+          range_next = base;
+          range_end = exhausted ? base : min(base + batch, n_in);
+        }
+        const unsigned take = min((unsigned)__popc(idle), range_end - range_next);
+        const unsigned rank = (unsigned)__popc(idle & lt_mask);
+        if ((idle >> lane & 1u) && rank < take) {
+          q = range_next + rank;
+          bool ok = true;
           float ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = -1;
           if (PRIMARY) {
             int px = 0, py = 0, ls = 0;
-            if (ok) path_pixel(P, q, px, py, ls);
-            ok = ok && px < P.width && py < P.height;
+            path_pixel(P, q, px, py, ls);
+            ok = px < P.width && py < P.height;
             if (ok) {
               // raytracer.c:644-677; rand_a == rand_b; exact 1/sqrt instead of rsqrt_ps
               const int s = P.sample0 + ls;
@@ -205,7 +215,7 @@ rt_trace_kernel(const __grid_constant__ StageParams P) {
               dz = (sc.view[2][0] * cx + sc.view[2][1] * cy + sc.view[2][2] * cz) * inv_len;
               ox = sc.view[0][3]; oy = sc.view[1][3]; oz = sc.view[2][3];       // raytracer.c:612
             }
-          } else if (ok) {
+          } else {
             const float4 a = P.q.ray_a[q], b = P.q.ray_b[q];
             ox = a.x; oy = a.y; oz = a.z; dx = a.w; dy = b.x; dz = b.y;
           }
@@ -213,8 +223,10 @@ rt_trace_kernel(const __grid_constant__ StageParams P) {
             walk_begin(w, sc, ox, oy, oz, dx, dy, dz);
             has_ray = true;
             c_rays++;
+            if (walk_misses_root(w, sc)) { w.done = true; c_nodes++; }      // the root visit, nothing entered
           }
         }
+        range_next += take;
       }
       if (__ballot_sync(RT_FULL, has_ray) == 0) break;
     }
@@ -267,7 +279,10 @@ rt_miss_kernel(const __grid_constant__ StageParams P) {
 // raytracer.c:514-552 for one hit: attribute interpolation (:164-182), back-face
 // pass-through, BSDF, emission/tint update, next origin.  Survivors go to the RAY
 // queue of bounce + 1; paths that terminate or exhaust max_bounces (:557) write rad.
-__global__ void __launch_bounds__(256)
+#ifndef RT_SHADE_MIN_BLOCKS
+#define RT_SHADE_MIN_BLOCKS 3
+#endif
+__global__ void __launch_bounds__(256, RT_SHADE_MIN_BLOCKS)
 rt_shade_kernel(const __grid_constant__ StageParams P) {
   __shared__ float texel_lut[256];
   texel_lut[threadIdx.x] = (float)threadIdx.x / 255.999f;

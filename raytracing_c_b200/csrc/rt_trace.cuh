@@ -131,6 +131,18 @@ __device__ __forceinline__ void walk_begin(RayWalk &w, const SceneDev &sc, float
   w.hit_t = CUDART_INF_F; w.hit_u = 0; w.hit_v = 0; w.hit_slot = -1;
 }
 
+// A regular ray that misses the union of the root's child boxes misses every one of them: the union's
+// near planes are <= and its far planes >= each child's, and the slab arithmetic is monotonic, so
+// enter_child >= enter_union >= leave_union >= leave_child (same formulas, same rounding).  Such a
+// ray's walk is the root visit alone — 18 instructions instead of eight box tests and a selection.
+__device__ __forceinline__ bool walk_misses_root(const RayWalk &w, const SceneDev &sc) {
+  if (!w.regular) return false;
+  const float nx = (w.near_rows & 1u) ? sc.root_hi[0] : sc.root_lo[0], fx = (w.near_rows & 1u) ? sc.root_lo[0] : sc.root_hi[0];
+  const float ny = (w.near_rows & 2u) ? sc.root_hi[1] : sc.root_lo[1], fy = (w.near_rows & 2u) ? sc.root_lo[1] : sc.root_hi[1];
+  const float nz = (w.near_rows & 4u) ? sc.root_hi[2] : sc.root_lo[2], fz = (w.near_rows & 4u) ? sc.root_lo[2] : sc.root_hi[2];
+  return child_entry_regular(nx, ny, nz, fx, fy, fz, w.ox, w.oy, w.oz, w.ix, w.iy, w.iz, CUDART_INF_F) == CUDART_INF_F;
+}
+
 // One node step: (box-test the node just entered,) pick the next child; ends with a leaf to test,
 // a child to enter on the next step, or the walk done.
 __device__ __forceinline__ void walk_node_step(RayWalk &w, const SceneDev &sc, float4 *levels, unsigned &c_nodes) {
