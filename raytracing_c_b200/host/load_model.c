@@ -18,6 +18,27 @@
 #include "rt_host.h"
 #include "rt_json.h"
 
+#include <pthread.h>
+
+/* one texture decode, run on its own thread (see the images loop of the glTF loader) */
+typedef struct {
+  u8 const *bytes; size_t len;      /* embedded image, or */
+  char     *path;                   /* file next to the model */
+  Image    *out;
+  bool      ok, threaded;
+  pthread_t thread;
+  char      error[256];
+} Decode_Job;
+
+static void *decode_job_run(void *arg) {
+  Decode_Job *job = arg;
+  if (job->error[0]) return NULL;
+  job->ok = job->bytes ? rt_image_decode(job->bytes, job->len, job->out) : rt_load_texture(job->path, job->out);
+  if (!job->ok) snprintf(job->error, sizeof job->error, "%s", rt_host_last_error());   /* thread-local on the worker */
+  return NULL;
+}
+
+
 void rt_host_set_error(char const *msg);
 
 static u8 *slurp(char const *path, size_t *len) {
@@ -438,23 +459,37 @@ static bool load_gltf(char const *path, u8 *data, size_t len, Shader_Proc proc, 
   RT_Json *images = rt_json_get(g.root, "images");
   model->n_images = rt_json_len(images);
   model->images = calloc((size_t)model->n_images + 1, sizeof(Image));
+  /* The reference decodes the images one after the other (stb_image, driver.c:620-626); decoding
+   * four 2048x2048 JPEGs is the largest term of time-to-image once the render runs on GPUs, so each
+   * image gets its own thread here.  Results do not depend on the schedule. */
   bool ok = true;
-  for (isize i = 0; i < model->n_images && ok; i++) {
+  Decode_Job *jobs = calloc((size_t)model->n_images + 1, sizeof(Decode_Job));
+  for (isize i = 0; i < model->n_images; i++) {
     RT_Json *im = rt_json_at(images, i);
     isize bv_index = rt_json_int(rt_json_get(im, "bufferView"), -1);
     char const *uri = rt_json_str(rt_json_get(im, "uri"));
+    jobs[i].out = &model->images[i];
     if (bv_index >= 0) {
       RT_Json *bv = rt_json_at(rt_json_get(g.root, "bufferViews"), bv_index);
       isize buf = rt_json_int(rt_json_get(bv, "buffer"), 0);
       size_t off = (size_t)rt_json_int(rt_json_get(bv, "byteOffset"), 0), n = (size_t)rt_json_int(rt_json_get(bv, "byteLength"), 0);
-      ok = buf < g.n_buffers && g.buffers[buf] && off + n <= g.buffer_len[buf] && rt_image_decode(g.buffers[buf] + off, n, &model->images[i]);
+      if (buf < g.n_buffers && g.buffers[buf] && off + n <= g.buffer_len[buf]) { jobs[i].bytes = g.buffers[buf] + off; jobs[i].len = n; }
+      else snprintf(jobs[i].error, sizeof jobs[i].error, "bufferView %ld is out of range", (long)bv_index);
     } else if (uri && strncmp(uri, "data:", 5)) {
-      char *full = sibling_path(path, uri);
-      ok = rt_load_texture(full, &model->images[i]);
-      free(full);
-    } else ok = false;
-    if (!ok) fprintf(stderr, "Failed to load image %ld of '%s': %s\n", (long)i, path, rt_host_last_error());
+      jobs[i].path = sibling_path(path, uri);
+    } else snprintf(jobs[i].error, sizeof jobs[i].error, "image has neither a bufferView nor a file uri");
   }
+  for (isize i = 1; i < model->n_images; i++) jobs[i].threaded = pthread_create(&jobs[i].thread, NULL, decode_job_run, &jobs[i]) == 0;
+  for (isize i = 0; i < model->n_images; i++) {
+    if (jobs[i].threaded) pthread_join(jobs[i].thread, NULL);
+    else decode_job_run(&jobs[i]);
+    if (!jobs[i].ok) {
+      ok = false;
+      fprintf(stderr, "Failed to load image %ld of '%s': %s\n", (long)i, path, jobs[i].error);
+    }
+    free(jobs[i].path);
+  }
+  free(jobs);
 
   /* materials (driver.c:628-660); one extra default at the end */
   RT_Json *mats = rt_json_get(g.root, "materials");
