@@ -329,7 +329,7 @@ def run_gpu(args) -> None:
                 "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": dict(workload_config(args, f"spp-range split x{world}, NCCL reduce(sum) of the f32 accumulator to rank 0"),
                                l2="flushed between steps (256 MiB memset inside the timed region, ~0.05 ms)",
-                               chunk="the library renders as many samples of every pixel per wavefront chunk as its 32 Mi-path queues hold"),
+                               chunk="the library renders as many samples of every pixel per wavefront chunk as its 128 Mi-path queues hold (26.6 GB)"),
                 "clocks": clocks, "gpu_launches": timed_launches,
                 "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": upload_bytes,
                         "d2h_bytes_per_step": W * H * 3,

@@ -51,7 +51,8 @@ typedef struct {
   u32   user_seed;        /* rt_seed.h; default 0 */
   i32   sample_begin;     /* render samples [begin, end) of ctx->samples; end 0 = all */
   i32   sample_end;
-  i32   slice_samples;    /* samples per kernel launch (progress granularity); default 16 */
+  i32   slice_samples;    /* samples per progress slice of render_thread_proc (one wavefront chunk
+                           * never spans slices); default 64 */
   i32   keep_hit_ids;     /* record the primary-hit slot of sample `sample_begin` */
 } RT_GPU_Options;
 void rt_gpu_set_options(RT_GPU_Options const *options);
@@ -73,6 +74,8 @@ f64 rt_gpu_last_kernel_ms(void);                       /* CUDA-event time of the
  *      Stages: 0 trace (closest hit), 1 miss (environment), 2 shade (BSDF), 3 accumulate. ---- */
 void rt_gpu_stage_profile_enable(i32 on);
 int  rt_gpu_stage_profile_read(f64 ms[4], i64 launches[4]);
+/* the same split by bounce: slot = stage * 16 + min(bounce, 15) */
+int  rt_gpu_stage_profile_read_bounces(f64 ms[64], i64 launches[64]);
 
 /* ---- device-pointer level (all pointers are device memory; stream is a
  *      cudaStream_t passed as void*, NULL = the legacy default stream) ---- */

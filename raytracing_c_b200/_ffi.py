@@ -108,7 +108,7 @@ GPU_EXPORTS = [
     "rt_gpu_register_pbr_shader", "rt_gpu_register_background", "rt_gpu_pbr_shader_proc", "rt_gpu_background_proc",
     "rt_gpu_scene_upload", "rt_gpu_scene_release", "rt_gpu_set_options", "rt_gpu_get_options",
     "rt_gpu_read_accum", "rt_gpu_read_hit_ids", "rt_gpu_read_counters", "rt_gpu_last_launches",
-    "rt_gpu_last_kernel_ms", "rt_gpu_stage_profile_enable", "rt_gpu_stage_profile_read",
+    "rt_gpu_last_kernel_ms", "rt_gpu_stage_profile_enable", "rt_gpu_stage_profile_read", "rt_gpu_stage_profile_read_bounces",
     "rt_gpu_render_accum_device", "rt_gpu_resolve_device", "rt_gpu_denoise_device",
 ]
 
@@ -188,6 +188,7 @@ def gpu_lib() -> C.CDLL:
         lib.rt_gpu_stage_profile_enable.argtypes = [C.c_int32]
         lib.rt_gpu_stage_profile_enable.restype = None
         lib.rt_gpu_stage_profile_read.argtypes = [C.POINTER(C.c_double * 4), C.POINTER(C.c_int64 * 4)]
+        lib.rt_gpu_stage_profile_read_bounces.argtypes = [C.POINTER(C.c_double * 64), C.POINTER(C.c_int64 * 64)]
         lib.rt_gpu_render_accum_device.argtypes = [C.POINTER(Scene), isize, isize, isize, isize, isize, C.c_uint32,
                                                    C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.rt_gpu_resolve_device.argtypes = [C.c_void_p, isize, isize, isize, C.c_void_p, isize, C.c_int32, C.c_void_p]

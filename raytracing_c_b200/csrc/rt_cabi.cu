@@ -63,7 +63,7 @@ struct State {
   std::vector<Shader_Proc>     pbr_procs;
   std::vector<Background_Proc> bg_procs;
   std::map<const Scene *, DeviceScene> scenes;
-  RT_GPU_Options options{0, 0, 0, 16, 0};
+  RT_GPU_Options options{0, 0, 0, 64, 0};
   // buffers of the last entry-point render (parity hooks)
   float *d_accum = nullptr;   size_t accum_floats = 0;
   int   *d_hit_ids = nullptr; size_t hit_pixels = 0;
@@ -451,7 +451,7 @@ void rt_gpu_scene_release(Scene const *scene) {
 void rt_gpu_set_options(RT_GPU_Options const *options) {
   std::lock_guard<std::mutex> lock(g_mutex);
   g.options = *options;
-  if (g.options.slice_samples < 1) g.options.slice_samples = 16;
+  if (g.options.slice_samples < 1) g.options.slice_samples = 64;
 }
 
 void rt_gpu_get_options(RT_GPU_Options *options) {
@@ -522,14 +522,26 @@ void rt_gpu_stage_profile_enable(i32 on) {
   rt_stage_profile_enable(on);
 }
 
-int rt_gpu_stage_profile_read(f64 ms[4], i64 launches[4]) {
+int rt_gpu_stage_profile_read_bounces(f64 ms[64], i64 launches[64]) {
   std::lock_guard<std::mutex> lock(g_mutex);
-  long long n[RT_N_STAGES];
+  long long n[RT_N_STAGES * RT_STAGE_BOUNCES];
   int e = rt_stage_profile_read(ms, n);
   if (e) return fail("stage profile: %s", cudaGetErrorString((cudaError_t)e));
-  for (int i = 0; i < RT_N_STAGES; i++) launches[i] = n[i];
+  for (int i = 0; i < RT_N_STAGES * RT_STAGE_BOUNCES; i++) launches[i] = n[i];
   return 0;
 }
+
+int rt_gpu_stage_profile_read(f64 ms[4], i64 launches[4]) {
+  f64 all_ms[RT_N_STAGES * RT_STAGE_BOUNCES];
+  i64 all_n[RT_N_STAGES * RT_STAGE_BOUNCES];
+  if (rt_gpu_stage_profile_read_bounces(all_ms, all_n)) return 1;
+  for (int s = 0; s < RT_N_STAGES; s++) {
+    ms[s] = 0; launches[s] = 0;
+    for (int b = 0; b < RT_STAGE_BOUNCES; b++) { ms[s] += all_ms[s * RT_STAGE_BOUNCES + b]; launches[s] += all_n[s * RT_STAGE_BOUNCES + b]; }
+  }
+  return 0;
+}
+
 f64 rt_gpu_last_kernel_ms(void) { return g.last_kernel_ms; }
 
 // ------------------------------------------------------- reference entry points
@@ -556,7 +568,7 @@ static int render_owner(Rendering_Context *ctx, isize n_chunks) {
   const RT_GPU_Options opt = g.options;
   const isize s_begin = opt.sample_begin;
   const isize s_end = opt.sample_end > 0 ? opt.sample_end : ctx->samples;
-  const isize slice = opt.slice_samples > 0 ? opt.slice_samples : 16;
+  const isize slice = opt.slice_samples > 0 ? opt.slice_samples : 64;
 
   g.last_launches = 0;
   g.last_pixels = n_pixels;

@@ -19,6 +19,7 @@ int rt_render_blocks_per_sm(void);
 int rt_launch_texel_repack(const unsigned char *src, int width, int height, int stride, int components,
                            uchar4 *dst, cudaStream_t stream);
 // per-stage CUDA-event timing of rt_launch_render's kernels (off by default)
-enum { RT_STAGE_TRACE = 0, RT_STAGE_MISS, RT_STAGE_SHADE, RT_STAGE_ACCUMULATE, RT_N_STAGES };
+// slot = stage * RT_STAGE_BOUNCES + min(bounce, RT_STAGE_BOUNCES - 1)
+enum { RT_STAGE_TRACE = 0, RT_STAGE_MISS, RT_STAGE_SHADE, RT_STAGE_ACCUMULATE, RT_N_STAGES, RT_STAGE_BOUNCES = 16 };
 void rt_stage_profile_enable(int on);
-int  rt_stage_profile_read(double ms[RT_N_STAGES], long long launches[RT_N_STAGES]);
+int  rt_stage_profile_read(double ms[RT_N_STAGES * RT_STAGE_BOUNCES], long long launches[RT_N_STAGES * RT_STAGE_BOUNCES]);

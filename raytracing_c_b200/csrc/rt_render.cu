@@ -110,6 +110,9 @@ __device__ __forceinline__ unsigned warp_append(unsigned *count, bool want, unsi
 // lanes have finished, those lanes append their results to the HIT / MISS queues and take the
 // next rays, while the others keep their walk state.  PRIMARY: the ray is generated from the
 // path id — 32 consecutive ids are one 8x4 pixel tile at one sample index, so rays are coherent.
+#ifndef RT_MIN_BATCH
+#define RT_MIN_BATCH 4u
+#endif
 #ifndef RT_REFILL_MIN
 #define RT_REFILL_MIN 16
 #endif
@@ -136,7 +139,14 @@ rt_trace_kernel(const __grid_constant__ StageParams P) {
   // rays reserved per atomic: large queues amortise the round trip, small ones (late bounces)
   // spread over all warps of the grid
   const unsigned total_warps = gridDim.x * (RT_BLOCK / 32);
-  const unsigned batch = min(256u, max(32u, (n_in / (total_warps * 4u)) & ~31u));
+  unsigned batch = (n_in / (total_warps * 4u)) & ~31u;
+  if (batch > 256u) batch = 256u;
+  if (batch < 32u) {
+    // a short queue: one share per warp, so the kernel lasts as long as a few rays, not as 32 in lock step
+    batch = (n_in + total_warps - 1u) / total_warps;
+    if (batch < RT_MIN_BATCH) batch = RT_MIN_BATCH;
+    if (batch > 32u) batch = 32u;
+  }
 
   for (;;) {
     const unsigned walking = __ballot_sync(RT_FULL, has_ray && !w.done);
@@ -413,15 +423,17 @@ __global__ void rt_resolve_kernel(const float *__restrict__ accum, int width, in
 
 // ------------------------------------------------------------------- launchers
 #define RT_PATH_BYTES ((4 + 5 + 3 + 1) * sizeof(float4))       // ray + hit + miss + rad records of one path
-#define RT_CHUNK_PATHS_MAX (32u << 20)
+#define RT_CHUNK_PATHS_MAX (128u << 20)
 
 static size_t counts_bytes(int max_bounces) {
   size_t b = (size_t)(max_bounces + 1) * Q_STRIDE * sizeof(unsigned);
   return (b + 255) & ~(size_t)255;
 }
 
-// Paths per wavefront chunk: enough to fill the machine many times over, small enough that the
-// queues (208 B per path) stay a few GB.  RT_GPU_CHUNK_PATHS overrides it (tuning / tests).
+// Paths per wavefront chunk.  Every chunk pays a fixed ~1.3 ms (26 launches whose tails drain, late
+// bounces that last as long as their slowest ray), measured 3.56 / 4.22 / 4.61 / 4.77 Gsamples/s at
+// 16 / 32 / 64 / 128 Mi paths on helmet 1080p; 128 Mi paths = 26.6 GB of queues (208 B per path) of
+// the 180 GB on the device.  RT_GPU_CHUNK_PATHS overrides it (tuning / tests).
 static size_t chunk_paths_max() {
   if (const char *e = getenv("RT_GPU_CHUNK_PATHS")) {
     unsigned long long v = strtoull(e, nullptr, 10);
@@ -476,8 +488,8 @@ void rt_stage_profile_enable(int on) {
   g_stage_events.clear();
 }
 
-int rt_stage_profile_read(double ms[RT_N_STAGES], long long launches[RT_N_STAGES]) {
-  for (int i = 0; i < RT_N_STAGES; i++) { ms[i] = 0; launches[i] = 0; }
+int rt_stage_profile_read(double ms[RT_N_STAGES * RT_STAGE_BOUNCES], long long launches[RT_N_STAGES * RT_STAGE_BOUNCES]) {
+  for (int i = 0; i < RT_N_STAGES * RT_STAGE_BOUNCES; i++) { ms[i] = 0; launches[i] = 0; }
   for (StageEvent &e : g_stage_events) {
     cudaError_t err = cudaEventSynchronize(e.b);
     if (err != cudaSuccess) return (int)err;
@@ -551,20 +563,21 @@ int rt_launch_render(const RenderParams &p, int sm_count, void *workspace, size_
     P.hit_ids = (s0 == p.sample_begin) ? p.hit_ids : nullptr;
     cudaMemsetAsync(P.q.counts, 0, cb, stream);
     P.bounce = 0;
-    { StageTimer t(RT_STAGE_TRACE, stream); rt_trace_kernel<true><<<trace_grid, RT_BLOCK, level_bytes, stream>>>(P); }
+    { StageTimer t(RT_STAGE_TRACE * RT_STAGE_BOUNCES, stream); rt_trace_kernel<true><<<trace_grid, RT_BLOCK, level_bytes, stream>>>(P); }
     launches++;
     for (int b = 0; b < p.max_bounces; b++) {
       P.bounce = b;
+      const int bslot = b < RT_STAGE_BOUNCES ? b : RT_STAGE_BOUNCES - 1;
       if (b > 0) {
-        StageTimer t(RT_STAGE_TRACE, stream);
+        StageTimer t(RT_STAGE_TRACE * RT_STAGE_BOUNCES + bslot, stream);
         rt_trace_kernel<false><<<trace_grid, RT_BLOCK, level_bytes, stream>>>(P);
         launches++;
       }
-      { StageTimer t(RT_STAGE_MISS, stream);  rt_miss_kernel<<<flat_grid, 256, 0, stream>>>(P); }
-      { StageTimer t(RT_STAGE_SHADE, stream); rt_shade_kernel<<<flat_grid, 256, 0, stream>>>(P); }
+      { StageTimer t(RT_STAGE_MISS * RT_STAGE_BOUNCES + bslot, stream);  rt_miss_kernel<<<flat_grid, 256, 0, stream>>>(P); }
+      { StageTimer t(RT_STAGE_SHADE * RT_STAGE_BOUNCES + bslot, stream); rt_shade_kernel<<<flat_grid, 256, 0, stream>>>(P); }
       launches += 2;
     }
-    { StageTimer t(RT_STAGE_ACCUMULATE, stream); rt_accumulate_kernel<<<flat_grid, 256, 0, stream>>>(P); }
+    { StageTimer t(RT_STAGE_ACCUMULATE * RT_STAGE_BOUNCES, stream); rt_accumulate_kernel<<<flat_grid, 256, 0, stream>>>(P); }
     launches++;
   }
   if (n_launches) *n_launches += launches;

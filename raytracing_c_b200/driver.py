@@ -112,7 +112,7 @@ def image_view(pixels: np.ndarray) -> Image:
     return im
 
 
-def set_options(user_seed: int = 0, sample_begin: int = 0, sample_end: int = 0, slice_samples: int = 16,
+def set_options(user_seed: int = 0, sample_begin: int = 0, sample_end: int = 0, slice_samples: int = 64,
                 keep_hit_ids: bool = False) -> None:
     opt = GPUOptions(user_seed, sample_begin, sample_end, slice_samples, int(keep_hit_ids))
     gpu_lib().rt_gpu_set_options(C.byref(opt))

@@ -19,9 +19,10 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--model", default="helmet.glb")
 ap.add_argument("--width", type=int, default=1920)
 ap.add_argument("--height", type=int, default=1080)
-ap.add_argument("--spp", type=int, default=16)
+ap.add_argument("--spp", type=int, default=64)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--denoise", action="store_true")
+ap.add_argument("--stages", action="store_true", help="print CUDA-event time per stage and bounce of the last rep")
 args = ap.parse_args()
 
 gpu = gpu_lib()
@@ -31,6 +32,7 @@ loaded = driver.load_scene(os.path.join(ROOT, "assets", "models", args.model))
 driver.register_callbacks(loaded)
 scene = C.byref(loaded.scene)
 gpu_check(gpu.rt_gpu_scene_upload(scene))
+driver.set_options(slice_samples=args.spp)      # chunking is then bounded by RT_GPU_CHUNK_PATHS alone
 W, H = args.width, args.height
 accum = torch.zeros(W * H * 3, dtype=torch.float32, device="cuda")
 pixels = torch.zeros(W * H * 3, dtype=torch.uint8, device="cuda")
@@ -39,6 +41,8 @@ counters = torch.zeros(8, dtype=torch.int64, device="cuda")
 stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 for rep in range(args.reps):
     counters.zero_()
+    if args.stages and rep == args.reps - 1:
+        gpu.rt_gpu_stage_profile_enable(1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     gpu_check(gpu.rt_gpu_render_accum_device(scene, W, H, 0, args.spp, 8, 0, 0, accum.data_ptr(), None, None,
@@ -51,4 +55,10 @@ for rep in range(args.reps):
     ms = e0.elapsed_time(e1)
     c = counters.cpu().tolist()
     print(f"rep {rep}: render {ms:.3f} ms  {W * H * args.spp / ms / 1e3:.1f} Msamples/s  counters {c}", flush=True)
+if args.stages:
+    ms, n = (C.c_double * 64)(), (C.c_int64 * 64)()
+    gpu_check(gpu.rt_gpu_stage_profile_read_bounces(C.byref(ms), C.byref(n)))
+    for s, name in enumerate(["trace", "miss", "shade", "accumulate"]):
+        print(name, " ".join(f"b{b}:{ms[s * 16 + b] * 1e3:.0f}us" for b in range(16) if n[s * 16 + b]), flush=True)
+    print(f"sum of kernel times {sum(ms) :.3f} ms", flush=True)
 loaded.close()
