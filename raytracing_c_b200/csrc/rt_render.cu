@@ -201,6 +201,12 @@ rt_trace_kernel(const __grid_constant__ StageParams P) {
           exhausted = base >= n_in;
           range_next = base;
           range_end = exhausted ? base : min(base + batch, n_in);
+          // guided self-scheduling: shares shrink as the queue drains, so the kernel's last wave is
+          // short (a 256-ray share held by one warp while the others idle is ~8 steps of 32 rays)
+          if (batch > 32u) {
+            const unsigned share = ((n_in - range_end) / (total_warps * 2u)) & ~31u;
+            batch = share < 32u ? 32u : (share < batch ? share : batch);
+          }
         }
         const unsigned take = min((unsigned)__popc(idle), range_end - range_next);
         const unsigned rank = (unsigned)__popc(idle & lt_mask);
