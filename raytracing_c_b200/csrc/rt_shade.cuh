@@ -81,8 +81,10 @@ __device__ __forceinline__ V3 cosine_hemisphere(uint32_t &rng) {
   float angle  = (float)(rnd(rng) * 2 * RT_PI);
   float radius = __fsqrt_rn(rnd(rng));
   V3 d;
-  d.x = rt_sinf(angle) * radius;
-  d.y = rt_cosf(angle) * radius;
+  float sn, cs;
+  rt_sincosf(angle, &sn, &cs);
+  d.x = sn * radius;
+  d.y = cs * radius;
   d.z = __fsqrt_rn(1 - radius * radius);
   return d;
 }
@@ -96,8 +98,10 @@ __device__ __forceinline__ V3 sample_vndf(V3 V, float ax, float ay, uint32_t &rn
 
   float r   = __fsqrt_rn(rnd(rng));
   float phi = (float)(2.0 * RT_PI * rnd(rng));
-  float t1  = r * rt_cosf(phi);
-  float t2  = r * rt_sinf(phi);
+  float sn, cs;
+  rt_sincosf(phi, &sn, &cs);
+  float t1  = r * cs;
+  float t2  = r * sn;
   float s   = (float)(0.5 * (1.0 + Vh.z));
   t2        = (float)((1.0 - s) * __fsqrt_rn((float)(1.0 - t1 * t1)) + s * t2);
 

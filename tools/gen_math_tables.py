@@ -42,5 +42,38 @@ def main():
         print(f"  E{k} = {float(LN2 ** k / Decimal(math.factorial(k))).hex()}")
 
 
+def asin_fit(degree=7):
+    """P(t) with asin(sqrt t) = sqrt t (1 + t P(t)) on [0, 1/4]: least squares on 400 Chebyshev nodes;
+    the target comes from the Taylor series in 60-digit decimals."""
+    import numpy as np
+
+    def series(t):
+        c, s, tk = Decimal(1), Decimal(0), Decimal(1)
+        for k in range(1, 400):
+            c = c * Decimal((2 * k - 1) ** 2) / Decimal(2 * k * (2 * k + 1))
+            term = c * tk
+            s += term
+            tk *= t
+            if term < Decimal(10) ** -50:
+                break
+        return s
+
+    n = 400
+    ts = [Decimal(0.125) * (1 + Decimal(math.cos(math.pi * (i + 0.5) / n))) for i in range(n)]
+    fit = np.polynomial.chebyshev.Chebyshev.fit(np.array([float(t) for t in ts]), np.array([float(series(t)) for t in ts]),
+                                                degree, domain=[0, 0.25])
+    coefs = fit.convert(kind=np.polynomial.Polynomial).coef
+    worst = Decimal(0)
+    for i in range(1, 2001):
+        t, p = Decimal(i) / Decimal(8000), Decimal(0)
+        for c in reversed(coefs):
+            p = p * t + Decimal(float(c))
+        worst = max(worst, abs((1 + t * p) - (1 + t * series(t))) / (1 + t * series(t)))
+    print(f"/* asin: P(t), degree {degree}, max relative error {float(worst):.3g}; highest power first */")
+    for c in reversed(coefs):
+        print(f"  {float(c).hex()},")
+
+
 if __name__ == "__main__":
     main()
+    asin_fit()
