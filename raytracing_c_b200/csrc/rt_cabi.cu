@@ -273,6 +273,17 @@ int build_device_scene(const Scene *scene, DeviceScene &ds) {
   if (upload(ds, nodes, &dev.nodes)) return 1;
   if (upload(ds, tri_pos, &dev.tri_pos)) return 1;
   if (upload(ds, records, &dev.tri_rec)) return 1;
+  {
+    // camera-relative copies for the primary trace, filled by rt_camera_relative_kernel at every render
+    void *p = nullptr;
+    const size_t node_bytes = nodes.size() * sizeof(float), tri_bytes = (size_t)n_slots * 4 * sizeof(float4);
+    if (pool_alloc(&p, node_bytes)) return 1;
+    ds.allocations.push_back({p, node_bytes}); ds.bytes += node_bytes;
+    dev.nodes_rel = static_cast<float *>(p);
+    if (pool_alloc(&p, tri_bytes)) return 1;
+    ds.allocations.push_back({p, tri_bytes}); ds.bytes += tri_bytes;
+    dev.tri_rel = static_cast<float4 *>(p);
+  }
   if (upload(ds, materials, &dev.materials)) return 1;
   if (upload(ds, textures, &dev.textures)) return 1;
   dev.env_texture = env_slot;

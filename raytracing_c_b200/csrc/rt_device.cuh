@@ -46,6 +46,8 @@ struct SceneDev {
   const float       *nodes;
   const float4      *tri_pos;
   const float4      *tri_rec;
+  float             *nodes_rel;      // nodes minus the camera origin, refreshed per render (primary rays)
+  float4            *tri_rel;        // float4[n_slots][4]: (o-p0, e1.x)(e1.yz, e2.xy)(e2.z, (o-p0) x e1)(e2 . that, -, -, -)
   const MaterialDev *materials;
   const TextureDev  *textures;
   int                env_texture;

@@ -104,6 +104,33 @@ __device__ __forceinline__ unsigned warp_append(unsigned *count, bool want, unsi
   return base + (unsigned)__popc(mask & ((1u << lane) - 1u));
 }
 
+// ------------------------------------------------------------ camera-relative scene
+// All primary rays start at the camera origin o (raytracer.c:612).  Everything in the slab and
+// triangle tests that depends on o but not on the direction — (plane - o) per node, and per triangle
+// tv = o - p0, qv = tv x e1, e2 . qv (raytracer.c:123-135) — is evaluated here once per render with the
+// same f32 expressions the per-ray code uses, so the primary trace reads constants instead.
+__global__ void rt_camera_relative_kernel(const SceneDev sc) {
+  const float ox = sc.view[0][3], oy = sc.view[1][3], oz = sc.view[2][3];
+  const int n_node_floats = sc.n_internal * 48;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_node_floats + sc.n_slots; i += gridDim.x * blockDim.x) {
+    if (i < n_node_floats) {
+      const int row = (i % 48) / 8;                     // rows: min x y z, max x y z
+      const float o = (row % 3 == 0) ? ox : (row % 3 == 1) ? oy : oz;
+      sc.nodes_rel[i] = sc.nodes[i] - o;
+    } else {
+      const int slot = i - n_node_floats;
+      const float4 A = sc.tri_pos[3 * slot], B = sc.tri_pos[3 * slot + 1], C = sc.tri_pos[3 * slot + 2];
+      const float e1x = A.w, e1y = B.x, e1z = B.y, e2x = B.z, e2y = B.w, e2z = C.x;
+      const float tvx = ox - A.x, tvy = oy - A.y, tvz = oz - A.z;
+      const float qvx = tvy * e1z - tvz * e1y, qvy = tvz * e1x - tvx * e1z, qvz = tvx * e1y - tvy * e1x;
+      sc.tri_rel[4 * slot + 0] = make_float4(tvx, tvy, tvz, e1x);
+      sc.tri_rel[4 * slot + 1] = B;
+      sc.tri_rel[4 * slot + 2] = make_float4(e2z, qvx, qvy, qvz);
+      sc.tri_rel[4 * slot + 3] = make_float4(e2x * qvx + e2y * qvy + e2z * qvz, 0, 0, 0);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------- trace
 // Persistent warps pull rays from the input queue (the GPU form of the reference's atomic
 // 32x32 chunk queue, raytracer.c:619-627) and keep their lanes full: whenever RT_REFILL_MIN
@@ -239,7 +266,7 @@ rt_trace_kernel(const __grid_constant__ StageParams P) {
             walk_begin(w, sc, ox, oy, oz, dx, dy, dz);
             has_ray = true;
             c_rays++;
-            if (walk_misses_root(w, sc)) { w.done = true; c_nodes++; }      // the root visit, nothing entered
+            if (walk_misses_root<PRIMARY>(w, sc)) { w.done = true; c_nodes++; }      // the root visit, nothing entered
           }
         }
         range_next += take;
@@ -252,9 +279,9 @@ rt_trace_kernel(const __grid_constant__ StageParams P) {
     const unsigned want_leaf = __ballot_sync(RT_FULL, w.leaf >= 0);
     const unsigned want_node = __ballot_sync(RT_FULL, has_ray && !w.done && w.leaf < 0);
     if (__popc(want_node) >= __popc(want_leaf)) {
-      if (want_node >> lane & 1u) walk_node_step(w, sc, levels, c_nodes);
+      if (want_node >> lane & 1u) walk_node_step<PRIMARY>(w, sc, levels, c_nodes);
     } else {
-      walk_leaf(w, sc, c_leaves, c_accepts);
+      walk_leaf<PRIMARY>(w, sc, c_leaves, c_accepts);
     }
     __syncwarp();
   }
@@ -557,9 +584,10 @@ int rt_launch_render(const RenderParams &p, int sm_count, void *workspace, size_
   cap = (size_t)chunk * per_sample;
   bind_queues(P.q, static_cast<char *>(workspace), cb, cap);
 
+  rt_camera_relative_kernel<<<(unsigned)sm_count, 256, 0, stream>>>(p.scene);
   const unsigned trace_grid = (unsigned)(sm_count * g_trace_blocks_per_sm);     // persistent: one wave
   const unsigned flat_grid  = (unsigned)(sm_count * 8);
-  int launches = 0;
+  int launches = 1;
   for (int s0 = p.sample_begin; s0 < p.sample_end; s0 += chunk) {
     const int S = (p.sample_end - s0 < chunk) ? p.sample_end - s0 : chunk;
     P.sample0 = s0; P.n_samples = S;

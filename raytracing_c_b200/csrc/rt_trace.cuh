@@ -39,10 +39,14 @@ __device__ __forceinline__ float child_entry_any(float lox, float loy, float loz
 // of i alone.  The caller hands in the near and far plane per axis; the values — and therefore
 // enter, leave and the compare — are the reference's (a zero's sign can differ, but enter >= EPS
 // and leave is only compared).
+// REL: the planes are already relative to the ray origin (camera-relative node copy, see
+// rt_camera_relative_kernel) — the same f32 subtraction, done once per frame instead of per ray.
+template <bool REL>
 __device__ __forceinline__ float child_entry_regular(float nx, float ny, float nz, float fx, float fy, float fz,
                                                      float ox, float oy, float oz, float ix, float iy, float iz, float t_max) {
-  float enter = fmaxf(fmaxf((nx - ox) * ix, (ny - oy) * iy), fmaxf((nz - oz) * iz, RT_EPS));
-  float leave = fminf(fminf((fx - ox) * ix, (fy - oy) * iy), fminf((fz - oz) * iz, t_max));
+  if (!REL) { nx -= ox; ny -= oy; nz -= oz; fx -= ox; fy -= oy; fz -= oz; }
+  float enter = fmaxf(fmaxf(nx * ix, ny * iy), fmaxf(nz * iz, RT_EPS));
+  float leave = fminf(fminf(fx * ix, fy * iy), fminf(fz * iz, t_max));
   return (enter >= leave) ? CUDART_INF_F : enter;
 }
 
@@ -50,6 +54,7 @@ __device__ __forceinline__ float child_entry_regular(float nx, float ny, float n
 // A node is six 32-byte rows (min x/y/z, max x/y/z; child j in column j): twelve 16-byte loads,
 // warp-uniform for coherent rays.  near_rows packs, per axis, which row holds the near plane
 // (bit a set = direction negative on axis a = the max row is nearer).
+template <bool REL>
 __device__ __forceinline__ void node_entries_regular(const float4 *__restrict__ n4, unsigned near_rows,
                                                      float ox, float oy, float oz, float ix, float iy, float iz,
                                                      float t_max, float (&e)[8]) {
@@ -59,10 +64,10 @@ __device__ __forceinline__ void node_entries_regular(const float4 *__restrict__ 
   for (int h = 0; h < 2; h++) {
     float4 nx = __ldg(n4 + nxr + h), ny = __ldg(n4 + nyr + h), nz = __ldg(n4 + nzr + h);
     float4 fx = __ldg(n4 + fxr + h), fy = __ldg(n4 + fyr + h), fz = __ldg(n4 + fzr + h);
-    e[4 * h + 0] = child_entry_regular(nx.x, ny.x, nz.x, fx.x, fy.x, fz.x, ox, oy, oz, ix, iy, iz, t_max);
-    e[4 * h + 1] = child_entry_regular(nx.y, ny.y, nz.y, fx.y, fy.y, fz.y, ox, oy, oz, ix, iy, iz, t_max);
-    e[4 * h + 2] = child_entry_regular(nx.z, ny.z, nz.z, fx.z, fy.z, fz.z, ox, oy, oz, ix, iy, iz, t_max);
-    e[4 * h + 3] = child_entry_regular(nx.w, ny.w, nz.w, fx.w, fy.w, fz.w, ox, oy, oz, ix, iy, iz, t_max);
+    e[4 * h + 0] = child_entry_regular<REL>(nx.x, ny.x, nz.x, fx.x, fy.x, fz.x, ox, oy, oz, ix, iy, iz, t_max);
+    e[4 * h + 1] = child_entry_regular<REL>(nx.y, ny.y, nz.y, fx.y, fy.y, fz.y, ox, oy, oz, ix, iy, iz, t_max);
+    e[4 * h + 2] = child_entry_regular<REL>(nx.z, ny.z, nz.z, fx.z, fy.z, fz.z, ox, oy, oz, ix, iy, iz, t_max);
+    e[4 * h + 3] = child_entry_regular<REL>(nx.w, ny.w, nz.w, fx.w, fy.w, fz.w, ox, oy, oz, ix, iy, iz, t_max);
   }
 }
 
@@ -135,23 +140,28 @@ __device__ __forceinline__ void walk_begin(RayWalk &w, const SceneDev &sc, float
 // near planes are <= and its far planes >= each child's, and the slab arithmetic is monotonic, so
 // enter_child >= enter_union >= leave_union >= leave_child (same formulas, same rounding).  Such a
 // ray's walk is the root visit alone — 18 instructions instead of eight box tests and a selection.
+template <bool REL>
 __device__ __forceinline__ bool walk_misses_root(const RayWalk &w, const SceneDev &sc) {
   if (!w.regular) return false;
   const float nx = (w.near_rows & 1u) ? sc.root_hi[0] : sc.root_lo[0], fx = (w.near_rows & 1u) ? sc.root_lo[0] : sc.root_hi[0];
   const float ny = (w.near_rows & 2u) ? sc.root_hi[1] : sc.root_lo[1], fy = (w.near_rows & 2u) ? sc.root_lo[1] : sc.root_hi[1];
   const float nz = (w.near_rows & 4u) ? sc.root_hi[2] : sc.root_lo[2], fz = (w.near_rows & 4u) ? sc.root_lo[2] : sc.root_hi[2];
-  return child_entry_regular(nx, ny, nz, fx, fy, fz, w.ox, w.oy, w.oz, w.ix, w.iy, w.iz, CUDART_INF_F) == CUDART_INF_F;
+  // (the root box itself is not stored relative: six subtractions per ray, once)
+  return child_entry_regular<false>(nx, ny, nz, fx, fy, fz, w.ox, w.oy, w.oz, w.ix, w.iy, w.iz, CUDART_INF_F) == CUDART_INF_F;
 }
 
 // One node step: (box-test the node just entered,) pick the next child; ends with a leaf to test,
 // a child to enter on the next step, or the walk done.
+template <bool REL>
 __device__ __forceinline__ void walk_node_step(RayWalk &w, const SceneDev &sc, float4 *levels, unsigned &c_nodes) {
   float (&e)[8] = w.e;
   for (;;) {
     if (w.need_box) {
       const float4 *n4 = (const float4 *)(sc.nodes + (size_t)w.node * 48);
-      if (w.regular) node_entries_regular(n4, w.near_rows, w.ox, w.oy, w.oz, w.ix, w.iy, w.iz, w.hit_t, e);
-      else {
+      if (w.regular) {
+        if (REL) node_entries_regular<true >((const float4 *)(sc.nodes_rel + (size_t)w.node * 48), w.near_rows, 0, 0, 0, w.ix, w.iy, w.iz, w.hit_t, e);
+        else     node_entries_regular<false>(n4, w.near_rows, w.ox, w.oy, w.oz, w.ix, w.iy, w.iz, w.hit_t, e);
+      } else {
         const Entries8 r = node_entries_any(n4, w.ox, w.oy, w.oz, w.ix, w.iy, w.iz, w.hit_t);
         e[0] = r.lo.x; e[1] = r.lo.y; e[2] = r.lo.z; e[3] = r.lo.w; e[4] = r.hi.x; e[5] = r.hi.y; e[6] = r.hi.z; e[7] = r.hi.w;
       }
@@ -193,28 +203,50 @@ __device__ __forceinline__ void walk_node_step(RayWalk &w, const SceneDev &sc, f
 // p0 and the edges e1 = p1 - p0, e2 = p2 - p0 (the same f32 subtractions raytracer.c:116-122
 // does per ray, done once at upload).  Strict <, ascending j: the lowest lane wins a tie
 // inside the leaf and an earlier leaf wins across leaves (raytracer.c:15-32 with eps 0, :159).
+template <bool REL>
 __device__ __forceinline__ void walk_leaf(RayWalk &w, const SceneDev &sc, unsigned &c_leaves, unsigned &c_accepts) {
   if (w.leaf < 0) return;
-  const float4 *tp = sc.tri_pos + (size_t)w.leaf * 24;
   const float t_before = w.hit_t;
   c_leaves++;
-  #pragma unroll 1
-  for (int j = 0; j < 8; j++) {
-    const float4 A = __ldg(tp + 3 * j), B = __ldg(tp + 3 * j + 1), C = __ldg(tp + 3 * j + 2);
-    const float e1x = A.w, e1y = B.x, e1z = B.y, e2x = B.z, e2y = B.w, e2z = C.x;
-    float pvx = w.dy * e2z - w.dz * e2y, pvy = w.dz * e2x - w.dx * e2z, pvz = w.dx * e2y - w.dy * e2x;
-    float det = e1x * pvx + e1y * pvy + e1z * pvz;
-    float inv_det = 1.0f / det;
-    float tvx = w.ox - A.x, tvy = w.oy - A.y, tvz = w.oz - A.z;
-    float u = inv_det * (tvx * pvx + tvy * pvy + tvz * pvz);
-    // the reject mask is an OR (raytracer.c:137-152): a triangle that fails on u fails whatever v and t are
-    if ((u < -RT_EPS) | (u > 1 + RT_EPS)) continue;
-    float qvx = tvy * e1z - tvz * e1y, qvy = tvz * e1x - tvx * e1z, qvz = tvx * e1y - tvy * e1x;
-    float v = inv_det * (w.dx * qvx + w.dy * qvy + w.dz * qvz);
-    float t = inv_det * (e2x * qvx + e2y * qvy + e2z * qvz);
-    bool miss = (v < -RT_EPS) | (u + v > 1 + RT_EPS) | (t < RT_EPS);
-    // t <= 0 and NaN count as +inf (min_f32x8 with eps 0); NaN also fails the ordered compare
-    if (!miss && t > 0.0f && t < w.hit_t) { w.hit_t = t; w.hit_u = u; w.hit_v = v; w.hit_slot = w.leaf * 8 + j; }
+  if (REL) {
+    // camera-relative records: tv = o - p0, qv = tv x e1 and e2 . qv do not depend on the direction, so
+    // for rays that share the camera origin they are per-triangle constants (rt_camera_relative_kernel
+    // evaluates the very same f32 expressions once per frame)
+    const float4 *tp = sc.tri_rel + (size_t)w.leaf * 32;
+    #pragma unroll 1
+    for (int j = 0; j < 8; j++) {
+      const float4 A = __ldg(tp + 4 * j), B = __ldg(tp + 4 * j + 1), C = __ldg(tp + 4 * j + 2);
+      const float e1x = A.w, e1y = B.x, e1z = B.y, e2x = B.z, e2y = B.w, e2z = C.x;
+      float pvx = w.dy * e2z - w.dz * e2y, pvy = w.dz * e2x - w.dx * e2z, pvz = w.dx * e2y - w.dy * e2x;
+      float det = e1x * pvx + e1y * pvy + e1z * pvz;
+      float inv_det = 1.0f / det;
+      float u = inv_det * (A.x * pvx + A.y * pvy + A.z * pvz);
+      if ((u < -RT_EPS) | (u > 1 + RT_EPS)) continue;
+      float v = inv_det * (w.dx * C.y + w.dy * C.z + w.dz * C.w);
+      float t = inv_det * __ldg(&tp[4 * j + 3].x);
+      bool miss = (v < -RT_EPS) | (u + v > 1 + RT_EPS) | (t < RT_EPS);
+      if (!miss && t > 0.0f && t < w.hit_t) { w.hit_t = t; w.hit_u = u; w.hit_v = v; w.hit_slot = w.leaf * 8 + j; }
+    }
+  } else {
+    const float4 *tp = sc.tri_pos + (size_t)w.leaf * 24;
+    #pragma unroll 1
+    for (int j = 0; j < 8; j++) {
+      const float4 A = __ldg(tp + 3 * j), B = __ldg(tp + 3 * j + 1), C = __ldg(tp + 3 * j + 2);
+      const float e1x = A.w, e1y = B.x, e1z = B.y, e2x = B.z, e2y = B.w, e2z = C.x;
+      float pvx = w.dy * e2z - w.dz * e2y, pvy = w.dz * e2x - w.dx * e2z, pvz = w.dx * e2y - w.dy * e2x;
+      float det = e1x * pvx + e1y * pvy + e1z * pvz;
+      float inv_det = 1.0f / det;
+      float tvx = w.ox - A.x, tvy = w.oy - A.y, tvz = w.oz - A.z;
+      float u = inv_det * (tvx * pvx + tvy * pvy + tvz * pvz);
+      // the reject mask is an OR (raytracer.c:137-152): a triangle that fails on u fails whatever v and t are
+      if ((u < -RT_EPS) | (u > 1 + RT_EPS)) continue;
+      float qvx = tvy * e1z - tvz * e1y, qvy = tvz * e1x - tvx * e1z, qvz = tvx * e1y - tvy * e1x;
+      float v = inv_det * (w.dx * qvx + w.dy * qvy + w.dz * qvz);
+      float t = inv_det * (e2x * qvx + e2y * qvy + e2z * qvz);
+      bool miss = (v < -RT_EPS) | (u + v > 1 + RT_EPS) | (t < RT_EPS);
+      // t <= 0 and NaN count as +inf (min_f32x8 with eps 0); NaN also fails the ordered compare
+      if (!miss && t > 0.0f && t < w.hit_t) { w.hit_t = t; w.hit_u = u; w.hit_v = v; w.hit_slot = w.leaf * 8 + j; }
+    }
   }
   if (w.hit_t < t_before) c_accepts++;
   w.leaf = -1;
