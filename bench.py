@@ -126,7 +126,7 @@ def cpu_reference_rate(args, loaded=None, target_seconds: float = 15.0):
         t0 = time.perf_counter()
         oracle_ffi.render(loaded, args.width, args.height, 1, args.bounces, n_threads=cores, want_accum=False)
         t1 = time.perf_counter() - t0
-        spp = max(1, min(64, int(target_seconds / max(t1, 1e-3))))
+        spp = max(1, min(256, int(target_seconds / max(t1, 1e-3))))
         t0 = time.perf_counter()
         oracle_ffi.render(loaded, args.width, args.height, spp, args.bounces, n_threads=cores, want_accum=False)
         dt = time.perf_counter() - t0
@@ -355,7 +355,7 @@ def main() -> None:
     ap.add_argument("--spp", type=int, default=1024)
     ap.add_argument("--bounces", type=int, default=8)
     ap.add_argument("--slice", type=int, default=64, help="e2e leg: samples per progress slice of render_thread_proc")
-    ap.add_argument("--cpu-spp", type=int, default=4, help="--impl reference: spp of each bounded CPU step")
+    ap.add_argument("--cpu-spp", type=int, default=128, help="--impl reference: spp of each bounded CPU step (~6 s on 16 cores)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     import __graft_entry__ as entry
