@@ -208,45 +208,45 @@ __device__ __forceinline__ void walk_leaf(RayWalk &w, const SceneDev &sc, unsign
   if (w.leaf < 0) return;
   const float t_before = w.hit_t;
   c_leaves++;
-  if (REL) {
-    // camera-relative records: tv = o - p0, qv = tv x e1 and e2 . qv do not depend on the direction, so
-    // for rays that share the camera origin they are per-triangle constants (rt_camera_relative_kernel
-    // evaluates the very same f32 expressions once per frame)
-    const float4 *tp = sc.tri_rel + (size_t)w.leaf * 32;
-    #pragma unroll 1
-    for (int j = 0; j < 8; j++) {
-      const float4 A = __ldg(tp + 4 * j), B = __ldg(tp + 4 * j + 1), C = __ldg(tp + 4 * j + 2);
-      const float e1x = A.w, e1y = B.x, e1z = B.y, e2x = B.z, e2y = B.w, e2z = C.x;
-      float pvx = w.dy * e2z - w.dz * e2y, pvy = w.dz * e2x - w.dx * e2z, pvz = w.dx * e2y - w.dy * e2x;
-      float det = e1x * pvx + e1y * pvy + e1z * pvz;
-      float inv_det = 1.0f / det;
-      float u = inv_det * (A.x * pvx + A.y * pvy + A.z * pvz);
-      if ((u < -RT_EPS) | (u > 1 + RT_EPS)) continue;
-      float v = inv_det * (w.dx * C.y + w.dy * C.z + w.dz * C.w);
-      float t = inv_det * __ldg(&tp[4 * j + 3].x);
-      bool miss = (v < -RT_EPS) | (u + v > 1 + RT_EPS) | (t < RT_EPS);
-      if (!miss && t > 0.0f && t < w.hit_t) { w.hit_t = t; w.hit_u = u; w.hit_v = v; w.hit_slot = w.leaf * 8 + j; }
+  // The loop is rolled (unrolled it is 9 KB of code).  For incoherent rays it is software-pipelined by
+  // hand: the records of triangle j+1 are in flight while triangle j is tested, so a leaf pays one
+  // load latency, not eight (measured -3 % on the bounce kernels; coherent primary rays hit L1 and
+  // lose 3 % to the extra instructions, so they keep the plain loop).
+  constexpr int STRIDE = REL ? 4 : 3;
+  const float4 *tp = REL ? sc.tri_rel + (size_t)w.leaf * 32 : sc.tri_pos + (size_t)w.leaf * 24;
+  float4 A = __ldg(tp), B = __ldg(tp + 1), C = __ldg(tp + 2);
+  #pragma unroll 1
+  for (int j = 0; j < 8; j++) {
+    float4 An, Bn, Cn;
+    if (!REL) {
+      const float4 *next = tp + STRIDE * (j < 7 ? j + 1 : 7);
+      An = __ldg(next); Bn = __ldg(next + 1); Cn = __ldg(next + 2);
     }
-  } else {
-    const float4 *tp = sc.tri_pos + (size_t)w.leaf * 24;
-    #pragma unroll 1
-    for (int j = 0; j < 8; j++) {
-      const float4 A = __ldg(tp + 3 * j), B = __ldg(tp + 3 * j + 1), C = __ldg(tp + 3 * j + 2);
-      const float e1x = A.w, e1y = B.x, e1z = B.y, e2x = B.z, e2y = B.w, e2z = C.x;
-      float pvx = w.dy * e2z - w.dz * e2y, pvy = w.dz * e2x - w.dx * e2z, pvz = w.dx * e2y - w.dy * e2x;
-      float det = e1x * pvx + e1y * pvy + e1z * pvz;
-      float inv_det = 1.0f / det;
-      float tvx = w.ox - A.x, tvy = w.oy - A.y, tvz = w.oz - A.z;
-      float u = inv_det * (tvx * pvx + tvy * pvy + tvz * pvz);
-      // the reject mask is an OR (raytracer.c:137-152): a triangle that fails on u fails whatever v and t are
-      if ((u < -RT_EPS) | (u > 1 + RT_EPS)) continue;
-      float qvx = tvy * e1z - tvz * e1y, qvy = tvz * e1x - tvx * e1z, qvz = tvx * e1y - tvy * e1x;
+    const float e1x = A.w, e1y = B.x, e1z = B.y, e2x = B.z, e2y = B.w, e2z = C.x;
+    float pvx = w.dy * e2z - w.dz * e2y, pvy = w.dz * e2x - w.dx * e2z, pvz = w.dx * e2y - w.dy * e2x;
+    float det = e1x * pvx + e1y * pvy + e1z * pvz;
+    float inv_det = 1.0f / det;
+    // REL (camera-relative records): A.xyz is tv = o - p0 itself, C.yzw is qv = tv x e1 and the fourth
+    // vector holds e2 . qv — none depends on the direction, so for rays that share the camera origin
+    // they are per-triangle constants (rt_camera_relative_kernel evaluates the same f32 expressions)
+    float tvx = REL ? A.x : w.ox - A.x, tvy = REL ? A.y : w.oy - A.y, tvz = REL ? A.z : w.oz - A.z;
+    float u = inv_det * (tvx * pvx + tvy * pvy + tvz * pvz);
+    // the reject mask is an OR (raytracer.c:137-152): a triangle that fails on u fails whatever v and t are
+    if (!((u < -RT_EPS) | (u > 1 + RT_EPS))) {
+      float qvx, qvy, qvz, tq;
+      if (REL) { qvx = C.y; qvy = C.z; qvz = C.w; tq = __ldg(&tp[STRIDE * j + 3].x); }
+      else {
+        qvx = tvy * e1z - tvz * e1y; qvy = tvz * e1x - tvx * e1z; qvz = tvx * e1y - tvy * e1x;
+        tq = e2x * qvx + e2y * qvy + e2z * qvz;
+      }
       float v = inv_det * (w.dx * qvx + w.dy * qvy + w.dz * qvz);
-      float t = inv_det * (e2x * qvx + e2y * qvy + e2z * qvz);
+      float t = inv_det * tq;
       bool miss = (v < -RT_EPS) | (u + v > 1 + RT_EPS) | (t < RT_EPS);
       // t <= 0 and NaN count as +inf (min_f32x8 with eps 0); NaN also fails the ordered compare
       if (!miss && t > 0.0f && t < w.hit_t) { w.hit_t = t; w.hit_u = u; w.hit_v = v; w.hit_slot = w.leaf * 8 + j; }
     }
+    if (!REL) { A = An; B = Bn; C = Cn; }
+    else if (j < 7) { A = __ldg(tp + STRIDE * (j + 1)); B = __ldg(tp + STRIDE * (j + 1) + 1); C = __ldg(tp + STRIDE * (j + 1) + 2); }
   }
   if (w.hit_t < t_before) c_accepts++;
   w.leaf = -1;
