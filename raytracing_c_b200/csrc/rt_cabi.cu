@@ -336,7 +336,18 @@ int render_device_locked(const Scene *scene, isize width, isize height, isize s_
                                                 g.options.slice_samples);
   if (g.workspace_bytes < want) {
     CUDA_TRY(cudaStreamSynchronize(stream));      // an earlier launch may still read the old queues
-    if (grow(&g.d_workspace, &g.workspace_bytes, want)) return 1;
+    // the preferred size (up to 26.6 GB) is a throughput choice, not a requirement: on a device that
+    // cannot spare it, halve the request down to one sample of every pixel per chunk
+    const size_t floor_bytes = rt_render_workspace_bytes((int)width, (int)height, 1, (int)max_bounces, 1);
+    size_t ask = want;
+    for (;;) {
+      if (g.d_workspace) { cudaFree(g.d_workspace); g.d_workspace = nullptr; g.workspace_bytes = 0; }
+      if (cudaMalloc(&g.d_workspace, ask) == cudaSuccess) { g.workspace_bytes = ask; break; }
+      cudaGetLastError();                          // clear the allocation failure
+      g.d_workspace = nullptr;
+      if (ask <= floor_bytes) return fail("render: cannot allocate %zu bytes of path queues", ask);
+      ask = ask / 2 > floor_bytes ? ask / 2 : floor_bytes;
+    }
   }
   p.width = (int)width; p.height = (int)height;
   p.sample_begin = (int)s_begin; p.sample_end = (int)s_end; p.max_bounces = (int)max_bounces;
