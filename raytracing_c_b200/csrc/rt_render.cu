@@ -140,8 +140,15 @@ __global__ void rt_camera_relative_kernel(const SceneDev sc) {
 #ifndef RT_MIN_BATCH
 #define RT_MIN_BATCH 4u
 #endif
-#ifndef RT_REFILL_MIN
-#define RT_REFILL_MIN 16
+// Lanes that must have finished before the warp stops to emit results and take new rays.  The stop
+// itself costs ~300 instructions at partial width, waiting costs idle lanes: measured optimum is "all
+// 32" for primary rays (most finish in the same turn anyway; 9.17 / 8.60 / 8.20 / 8.08 ms per 64-spp
+// chunk at 8 / 16 / 24 / 32) and 20 for bounce rays (7.36 / 7.15 / 7.13 / 7.27 / 8.90 ms at 12 / 16 / 20 / 24 / 32).
+#ifndef RT_REFILL_MIN_PRIMARY
+#define RT_REFILL_MIN_PRIMARY 32
+#endif
+#ifndef RT_REFILL_MIN_BOUNCE
+#define RT_REFILL_MIN_BOUNCE 20
 #endif
 
 template <bool PRIMARY>
@@ -163,6 +170,7 @@ rt_trace_kernel(const __grid_constant__ StageParams P) {
   w.done = true; w.leaf = -1;
   bool     has_ray = false, exhausted = false;
   unsigned q = 0, range_next = 0, range_end = 0;
+  uint32_t seed0 = 0;                      // primary: the path's RNG seed, fixed when the ray is generated
   // rays reserved per atomic: large queues amortise the round trip, small ones (late bounces)
   // spread over all warps of the grid
   const unsigned total_warps = gridDim.x * (RT_BLOCK / 32);
@@ -177,22 +185,22 @@ rt_trace_kernel(const __grid_constant__ StageParams P) {
 
   for (;;) {
     const unsigned walking = __ballot_sync(RT_FULL, has_ray && !w.done);
-    if (walking == 0 || (!exhausted && __popc(~walking) >= RT_REFILL_MIN)) {
+    if (walking == 0 || (!exhausted && __popc(~walking) >= (PRIMARY ? RT_REFILL_MIN_PRIMARY : RT_REFILL_MIN_BOUNCE))) {
       // ---- emit: finished lanes hand their path to the next stage
       const bool fin = has_ray;        // every lane that is not walking and holds a ray has finished it
       const bool is_hit = fin && !(walking >> lane & 1u) && w.hit_slot >= 0;
       const bool is_miss = fin && !(walking >> lane & 1u) && w.hit_slot < 0;
       if (__any_sync(RT_FULL, is_hit | is_miss)) {
         unsigned path = q;
-        uint32_t rng = 0;
+        uint32_t rng = seed0;
         float4 tint = make_float4(1, 1, 1, 0), emis = make_float4(0, 0, 0, 0);
         if (is_hit | is_miss) {
           if (PRIMARY) {
-            int px, py, ls;
-            path_pixel(P, q, px, py, ls);
-            const int pixel = py * P.width + px;
-            rng = rt_path_seed((uint32_t)pixel, (uint32_t)(P.sample0 + ls), P.user_seed);
-            if (P.hit_ids && ls == 0) P.hit_ids[pixel] = w.hit_slot;
+            if (P.hit_ids) {                       // parity hook: primary-hit slot of the chunk's first sample
+              int px, py, ls;
+              path_pixel(P, q, px, py, ls);
+              if (ls == 0) P.hit_ids[py * P.width + px] = w.hit_slot;
+            }
           } else {
             const float4 b = P.q.ray_b[q];
             path = __float_as_uint(b.z);
@@ -257,6 +265,7 @@ rt_trace_kernel(const __grid_constant__ StageParams P) {
               dy = (sc.view[1][0] * cx + sc.view[1][1] * cy + sc.view[1][2] * cz) * inv_len;
               dz = (sc.view[2][0] * cx + sc.view[2][1] * cy + sc.view[2][2] * cz) * inv_len;
               ox = sc.view[0][3]; oy = sc.view[1][3]; oz = sc.view[2][3];       // raytracer.c:612
+              seed0 = rt_path_seed((uint32_t)(py * P.width + px), (uint32_t)s, P.user_seed);
             }
           } else {
             const float4 a = P.q.ray_a[q], b = P.q.ray_b[q];
