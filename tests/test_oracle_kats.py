@@ -96,6 +96,55 @@ def test_rt_math_pow_and_atan2_within_one_ulp():
     assert o.oracle_atan2f(0.0, -1.0) == np.float32(math.pi) and o.oracle_atan2f(0.0, 0.0) == 0.0
 
 
+def test_rt_math_dense_sweeps_stay_within_0_51_ulp():
+    """rt_math.h is the libm of BOTH sides, so its accuracy is part of the parity contract: dense sweeps
+    against binary64 libm, error measured in ulps of the binary32 result."""
+    o = oracle_ffi.lib()
+    rng = np.random.default_rng(11)
+
+    def ulps(got, want64):
+        want32 = want64.astype(np.float32)
+        return np.abs(got.astype(np.float64) - want64) / np.spacing(np.abs(want32)).astype(np.float64)
+
+    o.oracle_powf_array.argtypes = [C.c_void_p, C.c_float, C.c_void_p, C.c_ssize_t]
+    for y in (2.4, 1 / 2.4, 0.37, 7.3, -1.5):
+        x = np.concatenate([rng.uniform(0, 1, 200000), rng.uniform(1, 100, 50000), np.exp(rng.uniform(-60, 60, 50000))]).astype(np.float32)
+        out = np.zeros_like(x)
+        o.oracle_powf_array(x.ctypes.data, np.float32(y), out.ctypes.data, x.size)
+        want = np.power(x.astype(np.float64), np.float64(np.float32(y)))
+        ok = (want > 1e-37) & (want < 3e38)
+        assert ulps(out[ok], want[ok]).max() < 0.51
+    # subnormal base, overflow, underflow
+    assert o.oracle_powf(1e-41, 0.5) == pytest.approx(math.sqrt(1e-41), rel=1e-6)
+    assert o.oracle_powf(1e30, 2.4) == float("inf") and o.oracle_powf(1e-30, 2.4) == 0.0
+
+    o.oracle_asin_array.argtypes = [C.c_void_p, C.c_void_p, C.c_ssize_t]
+    x = np.concatenate([rng.uniform(-1, 1, 300000), [0.0, 1.0, -1.0, 0.5, -0.5, 0.99999994, 1e-20]]).astype(np.float32)
+    out = np.zeros_like(x)
+    o.oracle_asin_array(x.ctypes.data, out.ctypes.data, x.size)
+    nz = x != 0
+    assert ulps(out[nz], np.arcsin(x[nz].astype(np.float64))).max() < 0.51 and out[~nz].max() == 0
+    assert math.isnan(o.oracle_asinf(1.0000001))
+
+    o.oracle_atan2_array.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_ssize_t]
+    a, b = rng.uniform(-1, 1, 300000).astype(np.float32), rng.uniform(-1, 1, 300000).astype(np.float32)
+    out = np.zeros_like(a)
+    o.oracle_atan2_array(a.ctypes.data, b.ctypes.data, out.ctypes.data, a.size)
+    assert ulps(out, np.arctan2(a.astype(np.float64), b.astype(np.float64))).max() < 0.51
+
+
+def test_fused_sincos_is_bit_identical_to_the_separate_calls():
+    """The kernels call rt_sincosf where the reference calls sin_f32 and cos_f32 (driver.c:119-123,239-240)."""
+    o = oracle_ffi.lib()
+    sig = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_ssize_t]
+    o.oracle_sincos_array.argtypes = o.oracle_sincos_fused_array.argtypes = sig
+    x = np.random.default_rng(5).uniform(-10, 10, 200000).astype(np.float32)
+    s1, c1, s2, c2 = (np.zeros_like(x) for _ in range(4))
+    o.oracle_sincos_array(x.ctypes.data, s1.ctypes.data, c1.ctypes.data, x.size)
+    o.oracle_sincos_fused_array(x.ctypes.data, s2.ctypes.data, c2.ctypes.data, x.size)
+    assert np.array_equal(s1.view(np.uint32), s2.view(np.uint32)) and np.array_equal(c1.view(np.uint32), c2.view(np.uint32))
+
+
 def test_resolve_matches_numpy_restatement():
     """raytracer.c:700-716: /spp, clamp, sRGB OETF (common.h:90-92), *255.999, truncate."""
     rng = np.random.default_rng(5)
