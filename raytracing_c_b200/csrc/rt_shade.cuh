@@ -42,11 +42,12 @@ __device__ __noinline__ V3 sample_bilinear(const TextureDev &tex, const float *l
   return lerp3(top, bot, b);
 }
 
-// common.h:82-88
+// common.h:82-88.  The argument of the power is >= 0.055 / 1.055 (texel values are >= 0), so the
+// case analysis of rt_powf can be skipped: rt_powf_positive is bit-identical there.
 __device__ __forceinline__ V3 decode_srgb(V3 c) {
-  return mk3(rt_powf((c.x + 0.055f) / 1.055f, 2.4f),
-             rt_powf((c.y + 0.055f) / 1.055f, 2.4f),
-             rt_powf((c.z + 0.055f) / 1.055f, 2.4f));
+  return mk3(rt_powf_positive((c.x + 0.055f) / 1.055f, 2.4f),
+             rt_powf_positive((c.y + 0.055f) / 1.055f, 2.4f),
+             rt_powf_positive((c.z + 0.055f) / 1.055f, 2.4f));
 }
 
 // driver.c:95-104 (asin argument clamped: DESIGN.md deviation list)

@@ -133,6 +133,19 @@ def test_rt_math_dense_sweeps_stay_within_0_51_ulp():
     assert ulps(out, np.arctan2(a.astype(np.float64), b.astype(np.float64))).max() < 0.51
 
 
+def test_powf_positive_is_bit_identical_to_powf_on_its_domain():
+    """The sRGB decode on the device skips rt_powf's case analysis (rt_shade.cuh decode_srgb)."""
+    o = oracle_ffi.lib()
+    sig = [C.c_void_p, C.c_float, C.c_void_p, C.c_ssize_t]
+    o.oracle_powf_array.argtypes = o.oracle_powf_positive_array.argtypes = sig
+    x = np.concatenate([np.random.default_rng(9).uniform(0.05, 1.0, 500000), np.arange(256) / 255.999 / 1.055 + 0.055 / 1.055]).astype(np.float32)
+    a, b = np.zeros_like(x), np.zeros_like(x)
+    for y in (2.4, 1 / 2.4):
+        o.oracle_powf_array(x.ctypes.data, np.float32(y), a.ctypes.data, x.size)
+        o.oracle_powf_positive_array(x.ctypes.data, np.float32(y), b.ctypes.data, x.size)
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
 def test_fused_sincos_is_bit_identical_to_the_separate_calls():
     """The kernels call rt_sincosf where the reference calls sin_f32 and cos_f32 (driver.c:119-123,239-240)."""
     o = oracle_ffi.lib()
