@@ -16,6 +16,7 @@ f32 oracle_rand_f32(u32 *state)  { return rt_rand_f32(state); }
 
 void oracle_powf_array(f32 const *x, f32 y, f32 *out, isize n) { for (isize i = 0; i < n; i++) out[i] = rt_powf(x[i], y); }
 void oracle_powf_positive_array(f32 const *x, f32 y, f32 *out, isize n) { for (isize i = 0; i < n; i++) out[i] = rt_powf_positive(x[i], y); }
+void oracle_pow5_array(f32 const *x, f32 *out, isize n) { for (isize i = 0; i < n; i++) out[i] = rt_pow5f(x[i]); }
 void oracle_sincos_array(f32 const *x, f32 *s, f32 *c, isize n) { for (isize i = 0; i < n; i++) { s[i] = rt_sinf(x[i]); c[i] = rt_cosf(x[i]); } }
 void oracle_sincos_fused_array(f32 const *x, f32 *s, f32 *c, isize n) { for (isize i = 0; i < n; i++) rt_sincosf(x[i], &s[i], &c[i]); }
 void oracle_atan2_array(f32 const *y, f32 const *x, f32 *out, isize n) { for (isize i = 0; i < n; i++) out[i] = rt_atan2f(y[i], x[i]); }

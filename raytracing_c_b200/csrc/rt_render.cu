@@ -214,14 +214,12 @@ rt_trace_kernel(const __grid_constant__ StageParams P) {
         if (is_hit) {
           P.q.hit_a[hpos] = make_float4(w.ox, w.oy, w.oz, w.dx);
           P.q.hit_b[hpos] = make_float4(w.dy, w.dz, __uint_as_float(path), __uint_as_float(rng));
-          P.q.hit_c[hpos] = tint;
-          P.q.hit_d[hpos] = emis;
+          if (!PRIMARY) { P.q.hit_c[hpos] = tint; P.q.hit_d[hpos] = emis; }      // bounce 0: tint 1, emission 0, implied
           P.q.hit_h[hpos] = make_float4(w.hit_t, w.hit_u, w.hit_v, __int_as_float(w.hit_slot));
         }
         if (is_miss) {
           P.q.miss_a[mpos] = make_float4(w.dx, w.dy, w.dz, __uint_as_float(path));
-          P.q.miss_b[mpos] = tint;
-          P.q.miss_c[mpos] = emis;
+          if (!PRIMARY) { P.q.miss_b[mpos] = tint; P.q.miss_c[mpos] = emis; }
         }
         if (is_hit | is_miss) has_ray = false;
       }
@@ -315,9 +313,17 @@ rt_miss_kernel(const __grid_constant__ StageParams P) {
   const unsigned n = P.q.counts[P.bounce * Q_STRIDE + Q_MISSES];
   unsigned done = 0;
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const float4 a = P.q.miss_a[i], t = P.q.miss_b[i], e = P.q.miss_c[i];
+    const float4 a = P.q.miss_a[i];
     V3 env = environment(P.scene, texel_lut, mk3(a.x, a.y, a.z));
-    V3 radiance = add3(mul3(env, mk3(t.x, t.y, t.z)), mk3(e.x, e.y, e.z));
+    V3 radiance;
+    if (P.bounce == 0) {
+      // primary rays carry tint 1 and emission 0 (raytracer.c:507-510): their records are not stored;
+      // env * 1 + 0 is env bit for bit (a -0 channel would become +0, the environment is never negative)
+      radiance = env;
+    } else {
+      const float4 t = P.q.miss_b[i], e = P.q.miss_c[i];
+      radiance = add3(mul3(env, mk3(t.x, t.y, t.z)), mk3(e.x, e.y, e.z));
+    }
     P.q.rad[__float_as_uint(a.w)] = make_float4(radiance.x, radiance.y, radiance.z, 0);
     done++;
   }
@@ -353,10 +359,14 @@ rt_shade_kernel(const __grid_constant__ StageParams P) {
     unsigned path = 0;
     uint32_t rng = 0;
     if (active) {
-      const float4 a = P.q.hit_a[i], b = P.q.hit_b[i], c = P.q.hit_c[i], e = P.q.hit_d[i], h = P.q.hit_h[i];
+      const float4 a = P.q.hit_a[i], b = P.q.hit_b[i], h = P.q.hit_h[i];
       o = mk3(a.x, a.y, a.z); d = mk3(a.w, b.x, b.y);
       path = __float_as_uint(b.z); rng = __float_as_uint(b.w);
-      tint = mk3(c.x, c.y, c.z); emis = mk3(e.x, e.y, e.z);
+      tint = mk3(1, 1, 1); emis = mk3(0, 0, 0);            // bounce 0 (raytracer.c:507-510): not stored
+      if (P.bounce > 0) {
+        const float4 c = P.q.hit_c[i], e = P.q.hit_d[i];
+        tint = mk3(c.x, c.y, c.z); emis = mk3(e.x, e.y, e.z);
+      }
       const int slot = __float_as_int(h.w);
 
       const float4 *rec = sc.tri_rec + (size_t)slot * 7;

@@ -62,12 +62,14 @@ __device__ __noinline__ V3 environment(const SceneDev &sc, const float *lut, V3 
 __device__ __forceinline__ float luma(V3 c) { return dot3(c, mk3(0.2126f, 0.7152f, 0.0722f)); }
 
 // driver.c:204-210
-__device__ __forceinline__ float schlick1(float f0, float f90, float c) { return f0 + (f90 - f0) * rt_powf(1 - c, 5); }
+// pow_f32(x, 5) and pow_f32(x, 2) of the reference: rt_pow5f / x * x are what rt_powf returns for them
+__device__ __forceinline__ float schlick1(float f0, float f90, float c) { return f0 + (f90 - f0) * rt_pow5f(1 - c); }
 
 // driver.c:212-215
-__device__ __forceinline__ float ggx_d(float roughness, float n_h, float k) {
+__device__ __forceinline__ float ggx_d(float roughness, float n_h) {       // k = 2 at both call sites
   float a2 = roughness * roughness;
-  return (float)(a2 / (RT_PI * rt_powf((n_h * n_h) * (a2 * a2 - 1) + 1, k)));
+  float b  = (n_h * n_h) * (a2 * a2 - 1) + 1;
+  return (float)(a2 / (RT_PI * (b * b)));
 }
 
 // driver.c:217-221
@@ -176,7 +178,7 @@ __device__ __noinline__ void shade_pbr(const SceneDev &sc, const float *lut, int
 
   V3 f0 = lerp3(mk3(0.04f, 0.04f, 0.04f), base, metalness);
   float f90 = sel_min(1.0f, (1.0f / 0.04f) * luma(f0));
-  V3 F = add3(f0, scale3(sub3(mk3(f90, f90, f90), f0), rt_powf(1 - dot3(wi, h), 5)));
+  V3 F = add3(f0, scale3(sub3(mk3(f90, f90, f90), f0), rt_pow5f(1 - dot3(wi, h))));
 
   float w_diff = 1 - metalness;
   float w_spec = luma(F);
@@ -211,8 +213,8 @@ __device__ __noinline__ void shade_pbr(const SceneDev &sc, const float *lut, int
       n_v = sel_max(n_v, 0.001f);
       float n_h = sel_min(h.z, 0.99f);
       float a2  = roughness * roughness;
-      float pdf = (ggx_d(roughness, n_h, 2) * smith_g1(n_v, a2)) / sel_max(0.00001f, 4.0f * n_v);
-      float D = ggx_d(roughness, n_h, 2);
+      float pdf = (ggx_d(roughness, n_h) * smith_g1(n_v, a2)) / sel_max(0.00001f, 4.0f * n_v);
+      float D = ggx_d(roughness, n_h);
       float G = smith_g1(n_v, a2) * smith_g1(n_l, a2);
       V3 spec = scale3(F, D * G / (4 * n_l * n_v));
       fx = spec.x * n_l; fy = spec.y * n_l; fz = spec.z * n_l;

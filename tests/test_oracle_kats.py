@@ -146,6 +146,22 @@ def test_powf_positive_is_bit_identical_to_powf_on_its_domain():
         assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
 
 
+def test_pow5_and_square_are_what_powf_returns():
+    """Schlick terms and the GGX denominator call pow_f32(x, 5) / pow_f32(x, 2) in the reference
+    (driver.c:204-214); the device code uses rt_pow5f(x) and x * x."""
+    o = oracle_ffi.lib()
+    o.oracle_powf_array.argtypes = [C.c_void_p, C.c_float, C.c_void_p, C.c_ssize_t]
+    o.oracle_pow5_array.argtypes = [C.c_void_p, C.c_void_p, C.c_ssize_t]
+    rng = np.random.default_rng(4)
+    x = np.concatenate([rng.uniform(-1.5, 1.5, 300000), [0.0, -0.0, 1.0, -1.0, 1e-30, -1e-30, 3e7, np.inf, -np.inf]]).astype(np.float32)
+    a, b = np.zeros_like(x), np.zeros_like(x)
+    o.oracle_powf_array(x.ctypes.data, 5.0, a.ctypes.data, x.size)
+    o.oracle_pow5_array(x.ctypes.data, b.ctypes.data, x.size)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    o.oracle_powf_array(x.ctypes.data, 2.0, a.ctypes.data, x.size)
+    assert np.array_equal(a.view(np.uint32), (x * x).view(np.uint32))
+
+
 def test_fused_sincos_is_bit_identical_to_the_separate_calls():
     """The kernels call rt_sincosf where the reference calls sin_f32 and cos_f32 (driver.c:119-123,239-240)."""
     o = oracle_ffi.lib()
