@@ -43,6 +43,7 @@ for rep in range(args.reps):
     counters.zero_()
     if args.stages and rep == args.reps - 1:
         gpu.rt_gpu_stage_profile_enable(1)
+    times = globals().setdefault("times", [])
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     gpu_check(gpu.rt_gpu_render_accum_device(scene, W, H, 0, args.spp, 8, 0, 0, accum.data_ptr(), None, None,
@@ -54,7 +55,12 @@ for rep in range(args.reps):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     c = counters.cpu().tolist()
+    times.append(ms)
     print(f"rep {rep}: render {ms:.3f} ms  {W * H * args.spp / ms / 1e3:.1f} Msamples/s  counters {c}", flush=True)
+if len(times) > 2:
+    t = sorted(times[1:])
+    print(f"render ms over reps 1..{len(times) - 1}: min {t[0]:.3f} median {t[len(t) // 2]:.3f} max {t[-1]:.3f}  "
+          f"=> {W * H * args.spp / t[0] / 1e3:.1f} Msamples/s best", flush=True)
 if args.stages:
     ms, n = (C.c_double * 64)(), (C.c_int64 * 64)()
     gpu_check(gpu.rt_gpu_stage_profile_read_bounces(C.byref(ms), C.byref(n)))
