@@ -281,14 +281,23 @@ rt_trace_kernel(const __grid_constant__ StageParams P) {
       if (__ballot_sync(RT_FULL, has_ray) == 0) break;
     }
 
-    // ---- one step for the majority: node steps and leaf tests are different code, so the warp runs
-    // whichever more lanes wait for and the others keep their state for a later turn
-    const unsigned want_leaf = __ballot_sync(RT_FULL, w.leaf >= 0);
-    const unsigned want_node = __ballot_sync(RT_FULL, has_ray && !w.done && w.leaf < 0);
-    if (__popc(want_node) >= __popc(want_leaf)) {
-      if (want_node >> lane & 1u) walk_node_step<PRIMARY>(w, sc, levels, c_nodes);
-    } else {
+    if (PRIMARY) {
+      // coherent rays reach their leaves in nearly the same number of steps: plain while-while — every
+      // lane walks until it holds a leaf (or is done), then the warp tests the triangles together
+      // (measured 2.8 % faster than voting for them)
+      while (has_ray && !w.done && w.leaf < 0) walk_node_step<PRIMARY>(w, sc, levels, c_nodes);
+      __syncwarp();
       walk_leaf<PRIMARY>(w, sc, c_leaves, c_accepts);
+    } else {
+      // incoherent rays: one step for the majority — node steps and leaf tests are different code, so the
+      // warp runs whichever more lanes wait for and the others keep their state for a later turn
+      const unsigned want_leaf = __ballot_sync(RT_FULL, w.leaf >= 0);
+      const unsigned want_node = __ballot_sync(RT_FULL, has_ray && !w.done && w.leaf < 0);
+      if (__popc(want_node) >= __popc(want_leaf)) {
+        if (want_node >> lane & 1u) walk_node_step<PRIMARY>(w, sc, levels, c_nodes);
+      } else {
+        walk_leaf<PRIMARY>(w, sc, c_leaves, c_accepts);
+      }
     }
     __syncwarp();
   }
