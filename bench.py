@@ -30,9 +30,20 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-MODEL = os.path.join(ROOT, "assets", "models", "helmet.glb")
+MODELS = os.path.join(ROOT, "assets", "models")
 METRIC = "Msamples/s (pixel*spp/s), helmet.glb 1920x1080"
 UNIT = "Msamples/s"
+# BASELINE.json's other configs, selectable with --workload for the multi-GPU sweeps (the default, and the only
+# one the driver's contract names, is the headline helmet frame)
+WORKLOADS = {
+    "helmet1080p": dict(model="helmet.glb", width=1920, height=1080, spp=1024, camera=None,
+                        describe="helmet.glb (15452 triangles, depth-4 8-ary BVH, 4x 2048^2 textures)"),
+    "tower4k": dict(model="tower.obj", width=3840, height=2160, spp=1024,
+                    camera=dict(eye=(0.0, 12.5, 40.0), target=(0.0, 12.5, 0.0)),
+                    describe="tower.obj (4320 triangles, depth-4 8-ary BVH, default material), camera (0,12.5,40)->(0,12.5,0)"),
+    "spheres": dict(model="spheres.glb", width=1024, height=1024, spp=1024, camera=None,
+                    describe="spheres.glb (4800 triangles, 5 factor-only materials), camera from the file"),
+}
 COUNTER_NAMES = ["rays", "nodes", "leaves", "accepts", "shades", "misses", "passthrough", "samples"]
 
 # FLOP model of SURVEY §8(d): per box test 25 lane-ops x 8, per triangle 57 x 8, +33 per accepted
@@ -49,8 +60,9 @@ def algorithmic_flops(c: dict) -> float:
 
 
 def workload_config(args, parallelism: str) -> dict:
-    return {"workload": f"helmet.glb {args.width}x{args.height} {args.spp}spp max_bounces {args.bounces}",
-            "model": "helmet.glb (15452 triangles, depth-4 8-ary BVH, 4x 2048^2 textures)",
+    wl = WORKLOADS[args.workload]
+    return {"workload": f"{wl['model']} {args.width}x{args.height} {args.spp}spp max_bounces {args.bounces}",
+            "model": wl["describe"],
             "environment": "procedural equirect 2048x1024 (reference background.png is not in its tree)",
             "seed_mode": "per-(pixel,sample) rt_path_seed, user_seed 0", "parallelism": parallelism}
 
@@ -106,11 +118,23 @@ class ClockSampler(threading.Thread):
                 "n_samples": len(s)}
 
 
+def metric_name(args) -> str:
+    return METRIC if args.workload == "helmet1080p" else \
+        f"Msamples/s (pixel*spp/s), {WORKLOADS[args.workload]['model']} {args.width}x{args.height}"
+
+
 def host_threads() -> int:
     try:
         return len(os.sched_getaffinity(0))
     except Exception:
         return os.cpu_count() or 1
+
+
+def load_workload(args, **procs):
+    from raytracing_c_b200 import driver
+    wl = WORKLOADS[args.workload]
+    cam = driver.look_at(**wl["camera"]) if wl["camera"] else None
+    return driver.load_scene(os.path.join(MODELS, wl["model"]), camera=cam, **procs)
 
 
 def cpu_reference_rate(args, loaded=None, target_seconds: float = 15.0):
@@ -120,7 +144,7 @@ def cpu_reference_rate(args, loaded=None, target_seconds: float = 15.0):
     from raytracing_c_b200 import driver
     own = loaded is None
     if own:
-        loaded = driver.load_scene(MODEL, shader_proc=oracle_ffi.shader_proc(), background_proc=oracle_ffi.background_proc())
+        loaded = load_workload(args, shader_proc=oracle_ffi.shader_proc(), background_proc=oracle_ffi.background_proc())
     cores = host_threads()
     try:
         t0 = time.perf_counter()
@@ -135,7 +159,7 @@ def cpu_reference_rate(args, loaded=None, target_seconds: float = 15.0):
             loaded.close()
     rate = args.width * args.height * spp / dt / 1e6
     return {"value": round(rate, 4), "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"helmet.glb {args.width}x{args.height} at {spp} spp ({dt:.1f} s of CPU work, AVX2 oracle, "
+            "sample": f"{WORKLOADS[args.workload]['model']} {args.width}x{args.height} at {spp} spp ({dt:.1f} s of CPU work, AVX2 oracle, "
                       f"reference chunk scheduler, {cores} threads)"}, spp, dt
 
 
@@ -145,7 +169,7 @@ def run_reference(args) -> None:
         return
     import oracle_ffi
     from raytracing_c_b200 import driver
-    loaded = driver.load_scene(MODEL, shader_proc=oracle_ffi.shader_proc(), background_proc=oracle_ffi.background_proc())
+    loaded = load_workload(args, shader_proc=oracle_ffi.shader_proc(), background_proc=oracle_ffi.background_proc())
     cores = host_threads()
     spp = args.cpu_spp
     per_step = []
@@ -159,7 +183,7 @@ def run_reference(args) -> None:
         loaded.close()
     total = sum(per_step)
     value = args.width * args.height * spp * len(per_step) / total / 1e6
-    line = {"impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": args.gpus,
+    line = {"impl": "reference", "metric": metric_name(args), "value": round(value, 4), "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * total / len(per_step), 3),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, "cpu"),
@@ -195,7 +219,7 @@ def run_gpu(args) -> None:
     slice_spp = args.slice
 
     t0 = time.perf_counter()
-    loaded = driver.load_scene(MODEL)          # Shader/Background procs = the GPU library's own identities
+    loaded = load_workload(args)               # Shader/Background procs = the GPU library's own identities
     t_load = time.perf_counter() - t0
     driver.register_callbacks(loaded)
     scene_ref = C.byref(loaded.scene)
@@ -324,7 +348,7 @@ def run_gpu(args) -> None:
         t0 = time.perf_counter()
         driver.save_image("/tmp/bench_helmet.png", host_pixels if world == 1 else pinned.numpy().reshape(H, W, 3))
         t_save = time.perf_counter() - t0
-        line = {"metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        line = {"metric": metric_name(args), "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": dict(workload_config(args, f"spp-range split x{world}, NCCL reduce(sum) of the f32 accumulator to rank 0"),
@@ -350,14 +374,18 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--width", type=int, default=1920)
-    ap.add_argument("--height", type=int, default=1080)
-    ap.add_argument("--spp", type=int, default=1024)
+    ap.add_argument("--workload", default="helmet1080p", choices=sorted(WORKLOADS))
+    ap.add_argument("--width", type=int, default=None)
+    ap.add_argument("--height", type=int, default=None)
+    ap.add_argument("--spp", type=int, default=None)
     ap.add_argument("--bounces", type=int, default=8)
     ap.add_argument("--slice", type=int, default=64, help="e2e leg: samples per progress slice of render_thread_proc")
     ap.add_argument("--cpu-spp", type=int, default=128, help="--impl reference: spp of each bounded CPU step (~6 s on 16 cores)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
+    for key in ("width", "height", "spp"):
+        if getattr(args, key) is None:
+            setattr(args, key, WORKLOADS[args.workload][key])
     import __graft_entry__ as entry
     if not (os.path.exists(os.path.join(ROOT, "raytracing_c_b200", "csrc", "libraytracer_gpu.so"))
             and os.path.exists(os.path.join(ROOT, "oracle", "liboracle.so"))):
