@@ -227,6 +227,30 @@ def test_wavefront_chunking_is_invisible(monkeypatch):
         loaded.close()
 
 
+def test_full_size_properties_helmet_1080p():
+    """BASELINE config 3 at its full resolution (the oracle is too slow there): size-independent properties.
+    (i) queue order is decided by atomics, the result is not: two runs are bit-identical;
+    (ii) every path ends exactly once: samples == W*H*spp == escaped + terminated;
+    (iii) rendering the two halves of the sample range and adding them equals the full render up to f32
+         addition order (the multi-GPU split), and splitting one render call into chunks changes nothing."""
+    loaded = load("helmet.glb")
+    try:
+        w, h, spp = 1920, 1080, 16
+        a = gpu_render(loaded, w, h, spp)
+        b = gpu_render(loaded, w, h, spp)
+        assert np.array_equal(a["accum"], b["accum"]) and np.array_equal(a["hit_ids"], b["hit_ids"])
+        c = a["counters"]
+        assert c["samples"] == w * h * spp and c["rays"] == c["samples"] + c["shades"] + c["passthrough"] - (c["samples"] - c["misses"])
+        lo = gpu_render(loaded, w, h, spp, sample_begin=0, sample_end=8)["accum"]
+        hi = gpu_render(loaded, w, h, spp, sample_begin=8, sample_end=16)["accum"]
+        np.testing.assert_allclose(lo + hi, a["accum"], rtol=2e-5, atol=1e-6)
+        chunked = gpu_render(loaded, w, h, spp, slice_samples=5)
+        assert np.array_equal(chunked["accum"], a["accum"]) and chunked["counters"] == c
+        assert not np.isnan(a["accum"]).any() and a["accum"].min() >= 0
+    finally:
+        loaded.close()
+
+
 def test_unregistered_shader_is_an_error():
     loaded = driver.load_scene(os.path.join(MODELS, "quad.obj"), shader_proc=0xDEAD0, background_proc=oracle_ffi.background_proc())
     try:
