@@ -137,59 +137,100 @@ def load_workload(args, **procs):
     return driver.load_scene(os.path.join(MODELS, wl["model"]), camera=cam, **procs)
 
 
-def cpu_reference_rate(args, loaded=None, target_seconds: float = 15.0):
-    """Times the CPU restatement (oracle; oracle/_ref when it exists) on all host threads on a bounded
-    sample of the SAME frame: full resolution, reduced spp (the rate does not depend on spp)."""
-    import oracle_ffi
-    from raytracing_c_b200 import driver
-    own = loaded is None
-    if own:
-        loaded = load_workload(args, shader_proc=oracle_ffi.shader_proc(), background_proc=oracle_ffi.background_proc())
-    cores = host_threads()
+class CpuRenderer:
+    """The CPU arm: the reference's OWN raytracer.c / driver.c (oracle/_ref/libref.so — its sources compiled
+    unmodified where they lie, over the stand-in for its un-vendored stdlib; built by oracle/Makefile where
+    /root/reference exists and shipped with the repo snapshot) when that file is present, `kind: "reference"`;
+    otherwise the oracle port, `kind: "port"`.  Either way N host threads enter render_thread_proc with one
+    context and pull 32x32 chunks from its atomic counter, exactly as the reference's driver starts them
+    (driver.c:793-803)."""
+
+    def __init__(self, args):
+        import oracle_ffi
+        self.kind, self._ref = "port", None
+        try:
+            import ref_ffi
+            if os.path.exists(ref_ffi.REF_LIB):
+                self._ref = ref_ffi.lib()
+                self.kind = "reference"
+        except Exception:
+            self._ref = None
+        if self._ref is not None:
+            procs = dict(shader_proc=self._ref.ref_shader_proc(), background_proc=self._ref.ref_background_proc())
+        else:
+            procs = dict(shader_proc=oracle_ffi.shader_proc(), background_proc=oracle_ffi.background_proc())
+        self.loaded = load_workload(args, **procs)
+        self.args, self.cores = args, host_threads()
+        self.what = ("the reference's raytracer.c + driver.c (oracle/_ref; its own per-thread RNG stream and rsqrt_ps), AVX2" if self._ref is not None
+                     else "AVX2 oracle port") + f", reference chunk scheduler, {self.cores} threads"
+
+    def render(self, spp: int) -> float:
+        """Seconds for one frame at `spp` samples per pixel."""
+        import numpy as np
+        a = self.args
+        t0 = time.perf_counter()
+        if self._ref is None:
+            import oracle_ffi
+            oracle_ffi.render(self.loaded, a.width, a.height, spp, a.bounces, n_threads=self.cores, want_accum=False)
+        else:
+            from raytracing_c_b200._ffi import RenderingContext
+            from raytracing_c_b200.driver import image_view
+            pixels = np.zeros((a.height, a.width, 3), dtype=np.uint8)
+            ctx = RenderingContext()
+            ctx.image = image_view(pixels)
+            ctx.scene = C.pointer(self.loaded.scene)
+            ctx.samples, ctx.max_bounces, ctx.n_threads, ctx._current_chunk = spp, a.bounces, self.cores, 0
+            threads = [threading.Thread(target=self._ref.render_thread_proc, args=(C.byref(ctx),)) for _ in range(self.cores)]
+            for t in threads:
+                t.start()
+            for t in threads:
+                t.join()
+            assert ctx.n_threads == 0
+        return time.perf_counter() - t0
+
+    def close(self):
+        self.loaded.close()
+
+
+def cpu_reference_rate(args, target_seconds: float = 15.0):
+    """Times the CPU arm on all host threads on a bounded sample of the SAME frame: full resolution, reduced spp
+    (the rate does not depend on spp)."""
+    cpu = CpuRenderer(args)
     try:
-        t0 = time.perf_counter()
-        oracle_ffi.render(loaded, args.width, args.height, 1, args.bounces, n_threads=cores, want_accum=False)
-        t1 = time.perf_counter() - t0
+        t1 = cpu.render(1)
         spp = max(1, min(256, int(target_seconds / max(t1, 1e-3))))
-        t0 = time.perf_counter()
-        oracle_ffi.render(loaded, args.width, args.height, spp, args.bounces, n_threads=cores, want_accum=False)
-        dt = time.perf_counter() - t0
+        dt = cpu.render(spp)
     finally:
-        if own:
-            loaded.close()
+        cpu.close()
     rate = args.width * args.height * spp / dt / 1e6
-    return {"value": round(rate, 4), "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{WORKLOADS[args.workload]['model']} {args.width}x{args.height} at {spp} spp ({dt:.1f} s of CPU work, AVX2 oracle, "
-                      f"reference chunk scheduler, {cores} threads)"}, spp, dt
+    return {"value": round(rate, 4), "unit": UNIT, "cores": cpu.cores, "kind": cpu.kind,
+            "sample": f"{WORKLOADS[args.workload]['model']} {args.width}x{args.height} at {spp} spp ({dt:.1f} s of CPU work; "
+                      f"{cpu.what})"}, spp, dt
 
 
 def run_reference(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import oracle_ffi
-    from raytracing_c_b200 import driver
-    loaded = load_workload(args, shader_proc=oracle_ffi.shader_proc(), background_proc=oracle_ffi.background_proc())
-    cores = host_threads()
+    cpu = CpuRenderer(args)
     spp = args.cpu_spp
     per_step = []
     try:
         for i in range(args.warmup + args.steps):
-            t0 = time.perf_counter()
-            oracle_ffi.render(loaded, args.width, args.height, spp, args.bounces, n_threads=cores, want_accum=False)
+            dt = cpu.render(spp)
             if i >= args.warmup:
-                per_step.append(time.perf_counter() - t0)
+                per_step.append(dt)
     finally:
-        loaded.close()
+        cpu.close()
     total = sum(per_step)
     value = args.width * args.height * spp * len(per_step) / total / 1e6
     line = {"impl": "reference", "metric": metric_name(args), "value": round(value, 4), "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * total / len(per_step), 3),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, "cpu"),
-            "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": cores, "kind": "port",
+            "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": cpu.cores, "kind": cpu.kind,
                              "sample": f"each step = the same frame at {spp} spp instead of {args.spp} "
-                                       f"(rate is spp-independent); AVX2 oracle, {cores} threads"},
+                                       f"(rate is spp-independent); {cpu.what}"},
             "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
