@@ -133,7 +133,7 @@ __global__ void rt_camera_relative_kernel(const SceneDev sc) {
 
 // ---------------------------------------------------------------------- trace
 // Persistent warps pull rays from the input queue (the GPU form of the reference's atomic
-// 32x32 chunk queue, raytracer.c:619-627) and keep their lanes full: whenever RT_REFILL_MIN
+// 32x32 chunk queue, raytracer.c:619-627) and keep their lanes full: whenever RT_REFILL_MIN_*
 // lanes have finished, those lanes append their results to the HIT / MISS queues and take the
 // next rays, while the others keep their walk state.  PRIMARY: the ray is generated from the
 // path id — 32 consecutive ids are one 8x4 pixel tile at one sample index, so rays are coherent.
