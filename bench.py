@@ -224,10 +224,13 @@ def run_reference(args) -> None:
         cpu.close()
     total = sum(per_step)
     value = args.width * args.height * spp * len(per_step) / total / 1e6
+    config = workload_config(args, "cpu")
+    config["sample"] = (f"each step renders the same frame at {spp} spp instead of {args.spp} (the rate is spp-independent: "
+                        f"every sample is an independent path, raytracer.c:687-696)")
     line = {"impl": "reference", "metric": metric_name(args), "value": round(value, 4), "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * total / len(per_step), 3),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, "cpu"),
+            "config": config,
             "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": cpu.cores, "kind": cpu.kind,
                              "sample": f"each step = the same frame at {spp} spp instead of {args.spp} "
                                        f"(rate is spp-independent); {cpu.what}"},
@@ -235,12 +238,82 @@ def run_reference(args) -> None:
     print(json.dumps(line), flush=True)
 
 
+def parity_mask(W, H, n_random=4096, seed=2026):
+    """The pixels of the frame that are checked against the oracle after the timed region: 4096 random ones and
+    four full scanlines (per-(pixel,sample) seeds make every pixel independent of the others)."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    mask = np.zeros((H, W), dtype=np.uint8)
+    mask.reshape(-1)[rng.choice(W * H, size=min(n_random, W * H), replace=False)] = 1
+    for y in (H // 8, H // 3, H // 2, (2 * H) // 3):
+        mask[y, :] = 1
+    return mask
+
+
+def parity_against_oracle(args, accum_host, pixels_host):
+    """rank 0, after the timed region: the REDUCED f32 accumulator of the last step (all GPUs' shares combined) and
+    the resolved u8 image against the CPU oracle on `parity_mask` at the full sample count."""
+    import numpy as np
+    import oracle_ffi
+    W, H, SPP, B = args.width, args.height, args.spp, args.bounces
+    procs = dict(shader_proc=oracle_ffi.shader_proc(), background_proc=oracle_ffi.background_proc())
+    loaded = load_workload(args, **procs)
+    try:
+        mask = parity_mask(W, H)
+        t0 = time.perf_counter()
+        ref = oracle_ffi.render(loaded, W, H, SPP, B, n_threads=host_threads(), pixel_mask=mask)
+        dt = time.perf_counter() - t0
+    finally:
+        loaded.close()
+    sel = mask.astype(bool)
+    a, b = accum_host.reshape(H, W, 3)[sel].astype(np.float64), ref["accum"][sel].astype(np.float64)
+    rel = np.abs(a - b) / np.maximum(np.abs(b), 1e-6)
+    u8 = (pixels_host.reshape(H, W, 3)[sel] != ref["pixels"][sel])
+    return {"pixels": int(sel.sum()), "spp": SPP, "max_rel": float(rel.max()), "frac_within_1e-3": float((rel <= 1e-3).mean()),
+            "bit_identical": bool(np.array_equal(accum_host.reshape(H, W, 3)[sel], ref["accum"][sel])),
+            "u8_mismatch": int(u8.any(axis=-1).sum()), "oracle_s": round(dt, 2),
+            "what": "NCCL/NVLink-reduced f32 accumulator of the last timed step vs the CPU oracle: 4096 random pixels + 4 scanlines"}
+
+
+def film_kernel_rates(gpu, gpu_check, torch, W, H, SPP, sptr, peak_gbs):
+    """The two HBM-streaming kernels of the frame, timed alone with CUDA events (burst peak applies)."""
+    dev = torch.device("cuda", torch.cuda.current_device())
+    accum = torch.rand(H * W * 3, dtype=torch.float32, device=dev) * SPP
+    px, px2 = torch.zeros(H * W * 3, dtype=torch.uint8, device=dev), torch.zeros(H * W * 3, dtype=torch.uint8, device=dev)
+    ptrs = (C.c_void_p * 1)(accum.data_ptr())
+    out = {}
+    for name, call, nbytes in (
+            ("resolve", lambda: gpu.rt_gpu_reduce_resolve_device(ptrs, 1, None, W, H, SPP, px.data_ptr(), W, 3, sptr), W * H * 15),
+            ("denoise", lambda: gpu.rt_gpu_denoise_device(px.data_ptr(), px2.data_ptr(), W, H, W, W, 3, sptr), W * H * 6)):
+        for _ in range(3):
+            gpu_check(call())
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 20
+        e0.record()
+        for _ in range(reps):
+            gpu_check(call())
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        out[name] = {"ms": round(ms, 4), "algorithmic_bytes": nbytes, "GB/s": round(gbs, 1),
+                     "frac_of_hbm_peak": round(gbs / peak_gbs, 4), "note": "back-to-back launches: the 25 MB working set stays in the 126 MB L2"}
+    return out
+
+
+def measured_peaks() -> dict:
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
 def run_gpu(args) -> None:
     import numpy as np
     import torch
     import torch.distributed as dist
     from raytracing_c_b200 import driver, gpu_lib
-    from raytracing_c_b200._ffi import gpu_check
+    from raytracing_c_b200._ffi import SPLIT_AUTO, SPLIT_CHUNKS, SPLIT_SAMPLES, gpu_check
 
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -254,11 +327,10 @@ def run_gpu(args) -> None:
     dev = torch.device("cuda", local)
 
     W, H, SPP, B = args.width, args.height, args.spp, args.bounces
-    if SPP % (8 * world):
-        raise SystemExit("spp must be a multiple of 8 x n_gpus (jitter batches are 8 samples, raytracer.c:641-697)")
-    s_begin, s_end = rank * SPP // world, (rank + 1) * SPP // world
+    split_req = {"auto": SPLIT_AUTO, "samples": SPLIT_SAMPLES, "chunks": SPLIT_CHUNKS}[args.split]
     slice_spp = args.slice
 
+    driver.use_pinned_host_buffers(not args.pageable)      # scene buffers in pinned memory: H2D is a DMA from them
     t0 = time.perf_counter()
     loaded = load_workload(args)               # Shader/Background procs = the GPU library's own identities
     t_load = time.perf_counter() - t0
@@ -271,24 +343,74 @@ def run_gpu(args) -> None:
     scene_bytes = int(gpu.rt_gpu_scene_device_bytes(scene_ref))
     upload_bytes = int(gpu.rt_gpu_scene_upload_bytes(scene_ref))
 
-    accum = torch.zeros(H * W * 3, dtype=torch.float32, device=dev)
+    # the accumulator and the counters are the library's own buffers (cudaMalloc: exportable over CUDA IPC)
+    accum_ptr, ctr_ptr = C.c_void_p(), C.c_void_p()
+    gpu_check(gpu.rt_gpu_accum_buffer(W, H, C.byref(accum_ptr)))
+    gpu_check(gpu.rt_gpu_counters_buffer(C.byref(ctr_ptr)))
+    total = torch.zeros(H * W * 3, dtype=torch.float32, device=dev)        # rank 0: the combined accumulator
     pixels = torch.zeros(H * W * 3, dtype=torch.uint8, device=dev)
-    counters = torch.zeros(8, dtype=torch.int64, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    flag = torch.zeros(1, dtype=torch.int32, device=dev)
     stream = torch.cuda.current_stream()
     sptr = C.c_void_p(stream.cuda_stream)
     launches = {"n": 0}
+    mode_used = C.c_int32(SPLIT_SAMPLES)
+
+    # ---- the cross-GPU film.  Default: rank 0's fused reduce+resolve kernel reads the other ranks' accumulators in
+    # place over NVLink (CUDA IPC mappings); two 4-byte NCCL all-reduces fence it (all shares finished / all shares read).
+    # --reduce nccl: dist.reduce of the 24.9 MB accumulators, then the resolve kernel.
+    reduce_how = "single GPU: resolve only"
+    part_ptrs = None
+    if world > 1:
+        reduce_how = "nccl"
+        if args.reduce == "p2p":
+            handle = C.create_string_buffer(64)
+            ok = gpu.rt_gpu_ipc_export(accum_ptr, handle) == 0
+            handles = [None] * world
+            dist.all_gather_object(handles, handle.raw if ok else None)
+            if all(h is not None for h in handles):
+                if rank == 0:
+                    ptrs = [accum_ptr.value]
+                    for r in range(1, world):
+                        p = C.c_void_p()
+                        if gpu.rt_gpu_ipc_open(handles[r], C.byref(p)) != 0:
+                            ptrs = None
+                            break
+                        ptrs.append(p.value)
+                    part_ptrs = (C.c_void_p * world)(*ptrs) if ptrs else None
+                opened = [rank != 0 or part_ptrs is not None]
+                dist.broadcast_object_list(opened, src=0)
+                if opened[0]:
+                    reduce_how = "p2p"
+                elif rank == 0:
+                    sys.stderr.write("bench.py: CUDA IPC mapping failed (%s); falling back to the NCCL reduce\n" %
+                                     gpu.rt_gpu_last_error().decode())
+    if reduce_how == "nccl":
+        accum_t = torch.zeros(H * W * 3, dtype=torch.float32, device=dev)   # NCCL needs a torch tensor: the render writes into it
+        accum_ptr = C.c_void_p(accum_t.data_ptr())
+
+    def fence():
+        dist.all_reduce(flag)            # stream-ordered: completes on a rank only after every rank reached it
 
     def step(timed: bool):
         flush.zero_()                                              # L2 flush between steps
         n0 = gpu.rt_gpu_last_launches()
-        # one call: the library cuts [s_begin, s_end) into chunks of as many samples as its path queues hold
-        gpu_check(gpu.rt_gpu_render_accum_device(scene_ref, W, H, s_begin, s_end, B, 0, 0, accum.data_ptr(),
-                                                 None, None, counters.data_ptr() if timed else None, sptr))
-        if world > 1:
-            dist.reduce(accum, dst=0, op=dist.ReduceOp.SUM)        # NCCL over NVLink: 24.9 MB f32
-        if rank == 0:
-            gpu_check(gpu.rt_gpu_resolve_device(accum.data_ptr(), W, H, SPP, pixels.data_ptr(), W, 3, sptr))
+        # one call: the library picks this rank's share of the frame and cuts it into wavefront chunks
+        gpu_check(gpu.rt_gpu_render_shard_device(scene_ref, W, H, SPP, B, 0, rank, world, split_req, C.byref(mode_used),
+                                                 accum_ptr, ctr_ptr if timed else None, sptr))
+        if world == 1:
+            one = (C.c_void_p * 1)(accum_ptr.value)
+            gpu_check(gpu.rt_gpu_reduce_resolve_device(one, 1, total.data_ptr(), W, H, SPP, pixels.data_ptr(), W, 3, sptr))
+        elif reduce_how == "p2p":
+            fence()
+            if rank == 0:
+                gpu_check(gpu.rt_gpu_reduce_resolve_device(part_ptrs, world, total.data_ptr(), W, H, SPP, pixels.data_ptr(), W, 3, sptr))
+            fence()
+        else:
+            dist.reduce(accum_t, dst=0, op=dist.ReduceOp.SUM)      # NCCL over NVLink: 24.9 MB f32
+            if rank == 0:
+                total.copy_(accum_t)
+                gpu_check(gpu.rt_gpu_resolve_device(accum_t.data_ptr(), W, H, SPP, pixels.data_ptr(), W, 3, sptr))
         launches["n"] += gpu.rt_gpu_last_launches() - n0
 
     def barrier():
@@ -300,6 +422,7 @@ def run_gpu(args) -> None:
         step(False)
     barrier()
     launches["n"] = 0
+    gpu_check(gpu.rt_gpu_counters_reset())        # the library's counter block is only ever added to
     gpu.rt_gpu_stage_profile_enable(1)
     sampler = ClockSampler(local)
     sampler.start()
@@ -325,54 +448,113 @@ def run_gpu(args) -> None:
     gpu.rt_gpu_stage_profile_enable(0)
     stage_names = ["trace", "miss", "shade", "accumulate"]
     kern_ms, n_kern = float(stage_ms[0]), int(stage_n[0])
-    ctr = dict(zip(COUNTER_NAMES, [int(v) for v in counters.cpu().tolist()]))
-    trace_flops = (FLOP_RAYGEN * ctr["samples"] + FLOP_NODE * ctr["nodes"] + FLOP_LEAF * ctr["leaves"] +
+    raw16 = (C.c_uint64 * 16)()
+    gpu_check(gpu.rt_gpu_read_counters_ex(raw16))
+    raw = [int(v) for v in raw16]
+    ctr = dict(zip(COUNTER_NAMES, raw[:8]))
+    root_misses, primary_rays = raw[8], raw[9]
+    trace_flops = (FLOP_RAYGEN * primary_rays + FLOP_NODE * ctr["nodes"] + FLOP_LEAF * ctr["leaves"] +
                    FLOP_ACCEPT * ctr["accepts"])
+    # the same with a root-union miss counted as the 18 lane-ops it costs here instead of a 200-op node visit
+    trace_flops_strict = trace_flops - (FLOP_NODE - 18.0) * root_misses
     flops_per_launch = trace_flops / max(n_kern, 1)
-    achieved_tflops = flops_per_launch / (kern_ms / max(n_kern, 1) * 1e-3) / 1e12
+    launch_s = kern_ms / max(n_kern, 1) * 1e-3
+    achieved_tflops = flops_per_launch / launch_s / 1e12
     peak_ops = float(gpu.rt_gpu_measure_fp32_issue())
-    traffic = None
-    prof = os.path.join(ROOT, "profiles", "dram_traffic.json")
+    peaks = measured_peaks()
+    hbm_peak = float(peaks.get("hbm_gbs", 6551.0))
+    # per-launch DRAM traffic and executed instructions come from the ncu capture of THIS command committed under
+    # profiles/ (tools/ncu_traffic.py writes the JSON from the CSV next to it); absent => null
+    traffic, ncu_info = None, None
+    prof = os.path.join(ROOT, "profiles", "r02_trace_traffic.json")
     if os.path.exists(prof):
         try:
-            traffic = json.load(open(prof)).get("rt_trace_kernel_bytes_per_launch")
+            ncu_info = json.load(open(prof))
+            traffic = ncu_info.get("rt_trace_kernel", {}).get("dram_bytes_per_launch")
         except Exception:
-            traffic = None
+            traffic, ncu_info = None, None
     cache_bytes = (BYTES_NODE * ctr["nodes"] + BYTES_LEAF * ctr["leaves"] + BYTES_ACCEPT * ctr["accepts"]) / max(n_kern, 1)
     all_ms = sum(float(v) for v in stage_ms)
+    executed = None
+    if ncu_info and ncu_info.get("rt_trace_kernel", {}).get("thread_inst_per_launch"):
+        t = ncu_info["rt_trace_kernel"]
+        executed = {"thread_inst_per_launch": t["thread_inst_per_launch"], "ncu_launch_ms": t.get("ms_per_launch"),
+                    "lane_ops_per_s_T": round(t["thread_inst_per_launch"] / launch_s / 1e12, 3),
+                    "frac_of_peak": round(t["thread_inst_per_launch"] / launch_s / peak_ops, 4) if peak_ops else None,
+                    "source": ncu_info.get("source"),
+                    "note": "ALL executed thread-instructions of the kernel (address arithmetic, selects, queue I/O included), "
+                            "from the committed ncu capture of this command, over this run's CUDA-event launch time"}
     roofline = {"kernel": "rt_trace_kernel", "bound": "fp32_issue (not hbm, not tensor: SURVEY 8d)",
                 "achieved": round(achieved_tflops, 3), "peak": round(peak_ops / 1e12, 3), "unit": "TFLOP/s",
                 "frac": round(achieved_tflops / (peak_ops / 1e12), 4) if peak_ops else None, "traffic": traffic,
+                "traffic_source": ncu_info.get("source") if ncu_info else None,
                 "peak_source": "measured live: non-fused FMUL+FADD issue rate (csrc/rt_peak.cu); MEASURED_PEAKS.json has no FP32 entry",
-                "flop_model": "SURVEY 8d, traversal terms: 40/sample ray-gen + 200/node + 456/leaf + 33/accept, from the kernels' own counters",
+                "flop_model": "SURVEY 8d, traversal terms: 40/primary ray + 200/node + 456/leaf + 33/accept, from the kernels' own counters",
                 "flops_per_launch": flops_per_launch, "launch_ms": round(kern_ms / max(n_kern, 1), 4), "launches": n_kern,
+                "root_union_misses": root_misses,
+                "frac_root_miss_as_18_ops": round(trace_flops_strict / max(n_kern, 1) / launch_s / peak_ops, 4) if peak_ops else None,
+                "executed": executed,
                 "cache_level_bytes_per_launch": cache_bytes,
                 "hbm_compulsory_bytes_per_step": scene_bytes + 2 * W * H * 12,
+                "hbm_achieved_GBps": round(traffic / launch_s / 1e9, 1) if traffic else None,
+                "hbm_peak_GBps": hbm_peak,
                 "stage_share_of_kernel_time": {k: round(float(stage_ms[i]) / all_ms, 4) if all_ms else None
                                                for i, k in enumerate(stage_names)},
                 "stage_launches": {k: int(stage_n[i]) for i, k in enumerate(stage_names)},
                 "whole_step": {"flops": algorithmic_flops(ctr) / args.steps, "kernel_ms": round(all_ms / args.steps, 3),
                                "achieved_tflops": round(algorithmic_flops(ctr) / (all_ms * 1e-3) / 1e12, 3) if all_ms else None},
                 "per_sample": {k: round(ctr[k] / max(ctr["samples"], 1), 3) for k in ("rays", "nodes", "leaves", "shades", "misses")}}
+    if rank == 0:
+        roofline.update(film_kernel_rates(gpu, gpu_check, torch, W, H, SPP, sptr, hbm_peak))
 
-    # ---- e2e: through render_thread_proc with HOST buffers (N=1), or its device-level pieces + NCCL (N>1)
+    # the combined accumulator and image of the last timed step, for the parity check below
+    accum_host = total.cpu().numpy() if rank == 0 else None
+    pixels_host = pixels.cpu().numpy() if rank == 0 else None
+
+    # ---- e2e: through render_thread_proc with HOST buffers (N=1), or its device-level pieces + the cross-GPU film (N>1);
+    # every step re-uploads the scene (H2D) and reads the image back (D2H)
     host_pixels = np.zeros((H, W, 3), dtype=np.uint8)
     pinned = torch.empty(H * W * 3, dtype=torch.uint8).pin_memory()
-    e2e_steps = max(1, min(args.steps, 2))
+    e2e_steps = max(1, min(args.steps, 3))
+    parts = {"upload_ms": [], "reduce_ms": [], "d2h_ms": []}
 
     def e2e_step():
-        gpu_check(gpu.rt_gpu_scene_upload(scene_ref))              # H2D: nodes, triangles, textures, environment
+        t_a = time.perf_counter()
+        gpu_check(gpu.rt_gpu_scene_upload(scene_ref))              # H2D: nodes, triangles, textures, environment (asynchronous)
+        parts["upload_ms"].append(1e3 * (time.perf_counter() - t_a))
         if world == 1:
             driver.set_options(slice_samples=slice_spp)
             driver.render(loaded, W, H, SPP, B, n_threads=1, out=host_pixels)   # D2H inside
+            bd = (C.c_double * 4)()
+            gpu.rt_gpu_last_frame_breakdown(C.byref(bd))
+            parts["reduce_ms"].append(bd[1])
+            parts["d2h_ms"].append(bd[2])
         else:
-            step(False)
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            gpu_check(gpu.rt_gpu_render_shard_device(scene_ref, W, H, SPP, B, 0, rank, world, split_req, C.byref(mode_used),
+                                                     accum_ptr, None, sptr))
+            r0.record(stream)
+            if reduce_how == "p2p":
+                fence()
+                if rank == 0:
+                    gpu_check(gpu.rt_gpu_reduce_resolve_device(part_ptrs, world, None, W, H, SPP, pixels.data_ptr(), W, 3, sptr))
+                fence()
+            else:
+                dist.reduce(accum_t, dst=0, op=dist.ReduceOp.SUM)
+                if rank == 0:
+                    gpu_check(gpu.rt_gpu_resolve_device(accum_t.data_ptr(), W, H, SPP, pixels.data_ptr(), W, 3, sptr))
+            r1.record(stream)
+            t_b = time.perf_counter()
             if rank == 0:
                 pinned.copy_(pixels, non_blocking=True)
             torch.cuda.synchronize()
+            parts["d2h_ms"].append(1e3 * (time.perf_counter() - t_b))      # includes waiting for the render to drain
+            parts["reduce_ms"].append(r0.elapsed_time(r1))
 
     e2e_step()
     barrier()
+    for v in parts.values():
+        v.clear()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         e2e_step()
@@ -381,25 +563,37 @@ def run_gpu(args) -> None:
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = W * H * SPP / float(e2e_s.item()) / 1e6
+    driver.set_options()
 
     if rank == 0:
+        parity = None
+        if not args.no_parity:
+            parity = parity_against_oracle(args, accum_host, pixels_host)
         cpu, cpu_spp, cpu_dt = (None, None, None)
         if world == 1 and not args.no_cpu:
             cpu, cpu_spp, cpu_dt = cpu_reference_rate(args)
         t0 = time.perf_counter()
         driver.save_image("/tmp/bench_helmet.png", host_pixels if world == 1 else pinned.numpy().reshape(H, W, 3))
         t_save = time.perf_counter() - t0
+        mode_name = {SPLIT_SAMPLES: "sample-range", SPLIT_CHUNKS: "32x32-chunk round-robin"}[mode_used.value]
+        film = {"p2p": "rank 0's fused reduce+resolve kernel reads the peers' accumulators over NVLink (CUDA IPC), two 4-byte NCCL all-reduces as fences",
+                "nccl": "NCCL reduce(sum) of the f32 accumulators to rank 0, then the resolve kernel"}.get(reduce_how, reduce_how)
+        mean = lambda v: round(sum(v) / len(v), 3) if v else None
         line = {"metric": metric_name(args), "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": dict(workload_config(args, f"spp-range split x{world}, NCCL reduce(sum) of the f32 accumulator to rank 0"),
+                "config": dict(workload_config(args, f"{mode_name} split x{world} (the library's policy, rt_gpu_render_shard_device); film: {film}"),
                                l2="flushed between steps (256 MiB memset inside the timed region, ~0.05 ms)",
-                               chunk="the library renders as many samples of every pixel per wavefront chunk as its 128 Mi-path queues hold (26.6 GB)"),
-                "clocks": clocks, "gpu_launches": timed_launches,
+                               chunk="the library renders as many samples of every pixel per wavefront chunk as its 128 Mi-path queues hold",
+                               host_buffers="pinned (rt_gpu_host_alloc)" if not args.pageable else "pageable (staged through a pinned ring)"),
+                "clocks": clocks, "gpu_launches": timed_launches, "parity": parity,
                 "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": upload_bytes,
                         "d2h_bytes_per_step": W * H * 3,
+                        "upload_ms": mean(parts["upload_ms"]), "reduce_ms": mean(parts["reduce_ms"]), "d2h_ms": mean(parts["d2h_ms"]),
+                        "ms_per_step": round(1e3 * float(e2e_s.item()), 3),
                         "how": "rt_gpu_scene_upload + render_thread_proc(host Image) per step" if world == 1 else
-                               "scene upload + per-rank render + NCCL reduce + resolve + D2H to pinned host on rank 0"},
+                               "scene upload + per-rank shard render + cross-GPU film + D2H to pinned host on rank 0, per step; "
+                               "upload_ms = host time of the asynchronous upload call, d2h_ms includes draining the render"},
                 "roofline": roofline, "cpu_baseline": cpu,
                 "time_to_image_s": {"load_decode_bvh": round(t_load, 3), "upload": round(t_upload, 3),
                                     "render_e2e": round(float(e2e_s.item()), 3), "png_encode": round(t_save, 3)}}
@@ -423,6 +617,10 @@ def main() -> None:
     ap.add_argument("--slice", type=int, default=64, help="e2e leg: samples per progress slice of render_thread_proc")
     ap.add_argument("--cpu-spp", type=int, default=128, help="--impl reference: spp of each bounded CPU step (~6 s on 16 cores)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the reduced accumulator")
+    ap.add_argument("--split", default="auto", choices=["auto", "samples", "chunks"], help="how a frame is split over GPUs")
+    ap.add_argument("--reduce", default="p2p", choices=["p2p", "nccl"], help="cross-GPU film: fused P2P reduce+resolve, or NCCL reduce")
+    ap.add_argument("--pageable", action="store_true", help="keep host scene buffers pageable (staged) instead of pinned")
     args = ap.parse_args()
     for key in ("width", "height", "spp"):
         if getattr(args, key) is None:

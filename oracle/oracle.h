@@ -53,6 +53,8 @@ typedef struct {
   f32  *per_sample;       /* optional W*H*(end-begin)*3 radiance of each sample */
   i32  *hit_ids;          /* optional W*H: padded slot of sample `sample_begin`'s primary hit, -1 = miss */
   u64   counters[8];      /* out: see ORACLE_CTR_* (summed over threads) */
+  u8 const *pixel_mask;   /* optional W*H: only pixels with a non-zero byte are rendered (per-(pixel,sample) seeds make any
+                           * subset independent: this is how full-size frames are spot-checked in seconds) */
 } Oracle_Options;
 
 enum {

@@ -325,6 +325,7 @@ static void *render_worker(void *arg) {
       for (isize x = x0; x < x0 + RT_CHUNK_SIZE && x < width; x++) {
         Color3 sum = v3(0, 0, 0);
         isize  pixel = x + y * width;
+        if (opt->pixel_mask && !opt->pixel_mask[pixel]) continue;
 
         for (isize batch = 0; batch < (samples + 7) / 8; batch++) {
           if (batch * 8 + 8 <= s_begin || batch * 8 >= s_end) continue;

@@ -92,7 +92,13 @@ class RenderingContext(C.Structure):
 
 class GPUOptions(C.Structure):
     _fields_ = [("user_seed", C.c_uint32), ("sample_begin", C.c_int32), ("sample_end", C.c_int32),
-                ("slice_samples", C.c_int32), ("keep_hit_ids", C.c_int32)]
+                ("slice_samples", C.c_int32), ("keep_hit_ids", C.c_int32), ("sample_range_set", C.c_int32),
+                ("split_mode", C.c_int32), ("reduce_mode", C.c_int32), ("pixel_rank", C.c_int32),
+                ("pixel_world", C.c_int32)]
+
+
+SPLIT_AUTO, SPLIT_SAMPLES, SPLIT_CHUNKS = 0, 1, 2
+REDUCE_P2P, REDUCE_NCCL = 0, 1
 
 
 TRIANGLE_AOS_BYTES = 112
@@ -103,11 +109,17 @@ GPU_EXPORTS = [
     "render_thread_proc", "rendering_context_is_finished", "rendering_context_finish", "lightmap_bake",
     "denoise_image",
     # rt_gpu.h
-    "rt_gpu_init", "rt_gpu_shutdown", "rt_gpu_last_error", "rt_gpu_sm_count", "rt_gpu_measure_fp32_issue",
+    "rt_gpu_init", "rt_gpu_init_devices", "rt_gpu_device_count", "rt_gpu_visible_devices", "rt_gpu_shutdown",
+    "rt_gpu_last_error", "rt_gpu_last_status", "rt_gpu_sm_count", "rt_gpu_measure_fp32_issue",
+    "rt_gpu_host_alloc", "rt_gpu_host_free", "rt_gpu_last_frame_breakdown",
+    "rt_gpu_shard_samples", "rt_gpu_shard_mode", "rt_gpu_shard_chunks",
+    "rt_gpu_render_shard_device", "rt_gpu_accum_buffer", "rt_gpu_ipc_export", "rt_gpu_ipc_open",
+    "rt_gpu_reduce_resolve_device",
     "rt_gpu_scene_device_bytes", "rt_gpu_scene_upload_bytes",
     "rt_gpu_register_pbr_shader", "rt_gpu_register_background", "rt_gpu_pbr_shader_proc", "rt_gpu_background_proc",
     "rt_gpu_scene_upload", "rt_gpu_scene_release", "rt_gpu_set_options", "rt_gpu_get_options",
-    "rt_gpu_read_accum", "rt_gpu_read_hit_ids", "rt_gpu_read_counters", "rt_gpu_last_launches",
+    "rt_gpu_read_accum", "rt_gpu_read_hit_ids", "rt_gpu_read_counters", "rt_gpu_counters_buffer", "rt_gpu_counters_reset",
+    "rt_gpu_read_counters_ex", "rt_gpu_last_launches",
     "rt_gpu_last_kernel_ms", "rt_gpu_stage_profile_enable", "rt_gpu_stage_profile_read", "rt_gpu_stage_profile_read_bounces",
     "rt_gpu_render_accum_device", "rt_gpu_resolve_device", "rt_gpu_denoise_device",
 ]
@@ -116,6 +128,7 @@ HOST_EXPORTS = [
     "scene_init", "scene_destroy", "rt_load_model_file", "rt_model_free", "rt_camera_default", "rt_camera_look_at",
     "rt_image_decode", "rt_load_texture", "rt_image_free", "rt_image_alloc", "rt_generate_background",
     "rt_save_image", "rt_save_png", "rt_save_qoi", "rt_save_ppm", "rt_host_last_error",
+    "rt_host_set_buffer_allocator", "rt_host_buffer_alloc", "rt_host_buffer_free",
 ]
 
 
@@ -158,6 +171,8 @@ def host_lib() -> C.CDLL:
             getattr(lib, name).restype = C.c_bool
             getattr(lib, name).argtypes = [C.c_char_p, C.POINTER(Image)]
         lib.rt_host_last_error.restype = C.c_char_p
+        lib.rt_host_set_buffer_allocator.argtypes = [C.c_void_p, C.c_void_p]
+        lib.rt_host_set_buffer_allocator.restype = None
         _host = lib
     return _host
 
@@ -169,6 +184,27 @@ def gpu_lib() -> C.CDLL:
             raise RuntimeError(f"{GPU_LIB} is missing: the CUDA extension must be built (no CPU fallback exists)")
         lib = C.CDLL(GPU_LIB)
         lib.rt_gpu_init.argtypes = [C.c_int]
+        lib.rt_gpu_init_devices.argtypes = [C.c_int, C.POINTER(C.c_int)]
+        lib.rt_gpu_host_alloc.restype = C.c_void_p
+        lib.rt_gpu_host_alloc.argtypes = [C.c_size_t]
+        lib.rt_gpu_host_free.argtypes = [C.c_void_p]
+        lib.rt_gpu_host_free.restype = None
+        lib.rt_gpu_last_frame_breakdown.argtypes = [C.POINTER(C.c_double * 4)]
+        lib.rt_gpu_last_frame_breakdown.restype = None
+        lib.rt_gpu_shard_samples.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+        lib.rt_gpu_shard_samples.restype = None
+        lib.rt_gpu_shard_mode.argtypes = [C.c_int32, C.c_int32, C.c_int32]
+        lib.rt_gpu_shard_mode.restype = C.c_int32
+        lib.rt_gpu_shard_chunks.argtypes = [C.c_int32, C.c_int32, isize, isize]
+        lib.rt_gpu_shard_chunks.restype = C.c_int32
+        lib.rt_gpu_render_shard_device.argtypes = [C.POINTER(Scene), isize, isize, isize, isize, C.c_uint32, C.c_int32,
+                                                   C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.c_void_p, C.c_void_p,
+                                                   C.c_void_p]
+        lib.rt_gpu_accum_buffer.argtypes = [isize, isize, C.POINTER(C.c_void_p)]
+        lib.rt_gpu_ipc_export.argtypes = [C.c_void_p, C.c_char_p]
+        lib.rt_gpu_ipc_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+        lib.rt_gpu_reduce_resolve_device.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.c_void_p, isize, isize, isize,
+                                                     C.c_void_p, isize, C.c_int32, C.c_void_p]
         lib.rt_gpu_last_error.restype = C.c_char_p
         lib.rt_gpu_measure_fp32_issue.restype = C.c_double
         lib.rt_gpu_scene_device_bytes.restype = isize
@@ -184,6 +220,8 @@ def gpu_lib() -> C.CDLL:
         lib.rt_gpu_read_accum.argtypes = [C.c_void_p, isize]
         lib.rt_gpu_read_hit_ids.argtypes = [C.c_void_p, isize]
         lib.rt_gpu_read_counters.argtypes = [C.c_void_p]
+        lib.rt_gpu_counters_buffer.argtypes = [C.POINTER(C.c_void_p)]
+        lib.rt_gpu_read_counters_ex.argtypes = [C.c_void_p]
         lib.rt_gpu_last_kernel_ms.restype = C.c_double
         lib.rt_gpu_stage_profile_enable.argtypes = [C.c_int32]
         lib.rt_gpu_stage_profile_enable.restype = None

@@ -1,379 +1,193 @@
 // rt_cabi.cu — the C ABI of libraytracer_gpu.so.
 //
-// Exports the reference's own entry points (raytracer.h:51-56, denoiser.h:4) plus
-// the additive rt_gpu_* calls declared in include/rt_gpu.h.  Host-side work here:
-//   * scene residency: flatten/regroup the host Scene into the device layout of
-//     rt_device.cuh once per Scene pointer (materials de-duplicated by
-//     Shader.data, textures by Image*, RGB8 -> RGBA8);
-//   * the reference's threading protocol around render_thread_proc
-//     (driver.c:793-818): the thread that claims chunk 0 owns the launch;
-//   * pinned staging + async copies for the image, CUDA-event timing.
-// There is no CPU fallback: every compute call fails if CUDA does.
+// Exports the reference's own entry points (raytracer.h:51-56, denoiser.h:4) plus the additive rt_gpu_* calls
+// declared in include/rt_gpu.h.  Host-side work here:
+//   * the reference's threading protocol around render_thread_proc (driver.c:793-818): the thread that claims
+//     chunk 0 owns the launch;
+//   * one frame over 1..N devices of this process: split (rt_multi.cu), per-device wavefront render
+//     (rt_render.cu), fused reduce + resolve on the first device, D2H of the u8 image;
+//   * per-call status: the reference's entry points return void, rt_gpu_last_status() says whether the last one failed.
+// Scene residency is rt_scene.cu.  There is no CPU fallback: every compute call fails if CUDA does.
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <chrono>
+#include <climits>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <cmath>
-#include <map>
-#include <mutex>
-#include <thread>
-#include <vector>
 #include <sched.h>
 
-#include "rt_gpu.h"
-#include "rt_kernels.h"
+#include "rt_state.h"
 #include "rt_gpu_internal.h"
 
-namespace {
+namespace rt {
 
+State g;
 std::mutex g_mutex;
-thread_local char g_error[512] = "";
+
+namespace {
+std::mutex g_error_mutex;
 char g_error_shared[512] = "";
+thread_local char g_error_copy[512] = "";
+std::atomic<int> g_status{0};
+}
 
 int fail(const char *fmt, ...) {
+  char text[512];
   va_list ap;
   va_start(ap, fmt);
-  vsnprintf(g_error, sizeof g_error, fmt, ap);
+  vsnprintf(text, sizeof text, fmt, ap);
   va_end(ap);
-  snprintf(g_error_shared, sizeof g_error_shared, "%s", g_error);
+  std::lock_guard<std::mutex> lock(g_error_mutex);
+  memcpy(g_error_shared, text, sizeof text);
   return 1;
 }
 
-#define CUDA_TRY(expr)                                                                      \
-  do {                                                                                      \
-    cudaError_t e_ = (expr);                                                                \
-    if (e_ != cudaSuccess) return fail("%s failed: %s", #expr, cudaGetErrorString(e_));     \
-  } while (0)
+void clear_error() {
+  std::lock_guard<std::mutex> lock(g_error_mutex);
+  g_error_shared[0] = 0;
+}
 
-struct DeviceScene {
-  SceneDev dev{};
-  std::vector<std::pair<void *, size_t>> allocations;
-  size_t bytes = 0;        // resident on the device
-  size_t h2d_bytes = 0;    // copied host -> device by the upload
-};
+}  // namespace rt
 
-struct State {
-  bool         ready = false;
-  int          device = -1;
-  int          sm_count = 0;
-  cudaStream_t stream = nullptr;
-  cudaEvent_t  ev0 = nullptr, ev1 = nullptr;
-  std::vector<Shader_Proc>     pbr_procs;
-  std::vector<Background_Proc> bg_procs;
-  std::map<const Scene *, DeviceScene> scenes;
-  RT_GPU_Options options{0, 0, 0, 64, 0};
-  // buffers of the last entry-point render (parity hooks)
-  float *d_accum = nullptr;   size_t accum_floats = 0;
-  int   *d_hit_ids = nullptr; size_t hit_pixels = 0;
-  unsigned long long *d_counters = nullptr;
-  void  *d_texel_stage = nullptr; size_t texel_stage_bytes = 0;  // raw texture bytes before the RGBA8 repack
-  void  *d_workspace = nullptr; size_t workspace_bytes = 0;     // wavefront path queues (rt_render.cu)
-  unsigned char *d_image = nullptr, *d_image2 = nullptr; size_t image_bytes = 0, image2_bytes = 0;
-  unsigned char *h_pinned = nullptr; size_t pinned_bytes = 0;
-  int    last_launches = 0;
-  double last_kernel_ms = 0;
-  bool   last_has_hit_ids = false;
-  size_t last_pixels = 0;
-} g;
+using namespace rt;
+
+namespace {
+
+double now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+int init_devices_locked(int n, const int *ids) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail("no CUDA device available (%s); libraytracer_gpu has no CPU fallback", cudaGetErrorString(e));
+  if (n < 1 || n > RT_MAX_PARTS) return fail("init: between 1 and %d devices, got %d", RT_MAX_PARTS, n);
+  std::vector<int> want;
+  for (int k = 0; k < n; k++) {
+    const int id = ids ? ids[k] : k;
+    if (id < 0 || id >= count || id >= RT_MAX_DEVICES) return fail("device %d out of range (%d visible)", id, count);
+    for (int prev : want) if (prev == id) return fail("device %d listed twice", id);
+    want.push_back(id);
+  }
+  if (g.ready) {
+    bool same = g.devs.size() == want.size();
+    for (size_t k = 0; same && k < want.size(); k++) same = g.devs[k].id == want[k];
+    if (same) return 0;
+    nccl_shutdown();
+    ipc_close_all();
+    for (Device &d : g.devs) release_device(d);
+    g.devs.clear();
+    g.ready = false;
+    g.peers_enabled = false;
+  }
+  g.devs.resize(want.size());
+  for (size_t k = 0; k < want.size(); k++) {
+    Device &d = g.devs[k];
+    CUDA_TRY(cudaSetDevice(want[k]));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, want[k]));
+    if (prop.major < 10) return fail("device %d is sm_%d%d; this library is built for sm_100a only", want[k], prop.major, prop.minor);
+    d.id = want[k];
+    d.sm_count = prop.multiProcessorCount;
+    d.l2_persist_max = prop.persistingL2CacheMaxSize > 0 ? (size_t)prop.persistingL2CacheMaxSize : 0;
+    d.l2_window_max = prop.accessPolicyMaxWindowSize > 0 ? (size_t)prop.accessPolicyMaxWindowSize : 0;
+    CUDA_TRY(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&d.copy, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreate(&d.ev0));
+    CUDA_TRY(cudaEventCreate(&d.ev1));
+    CUDA_TRY(cudaEventCreateWithFlags(&d.busy, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&d.done, cudaEventDisableTiming));
+  }
+  CUDA_TRY(cudaSetDevice(want[0]));
+  g.ready = true;
+  if (g.options.slice_samples < 1) g.options.slice_samples = 64;
+  return 0;
+}
 
 int ensure_init() {
   if (g.ready) return 0;
-  return rt_gpu_init(g.device < 0 ? 0 : g.device);
+  const int zero = 0;
+  return init_devices_locked(1, &zero);
 }
 
-// Device blocks of released scenes are kept and handed out again by exact size: re-uploading a
-// scene (per frame in an interactive host, per step in bench.py's end-to-end leg) then costs no
-// cudaMalloc / cudaFree (each a device-wide synchronisation).
-std::multimap<size_t, void *> g_block_pool;
-
-int pool_alloc(void **out, size_t bytes) {
-  auto it = g_block_pool.find(bytes);
-  if (it != g_block_pool.end()) { *out = it->second; g_block_pool.erase(it); return 0; }
-  CUDA_TRY(cudaMalloc(out, bytes));
+// Path-queue workspace of one device.  The preferred size (up to 26.6 GB) is a throughput choice, not a requirement:
+// on a device that cannot spare it the request is halved down to one sample of every pixel per chunk, and the size
+// that was refused is remembered so later calls do not walk the same ladder again.
+int ensure_workspace(Device &d, size_t want, size_t floor_bytes, cudaStream_t stream) {
+  if (d.workspace_bytes >= want) return 0;
+  if (d.workspace_denied && want >= d.workspace_denied && d.workspace_bytes >= floor_bytes) return 0;
+  CUDA_TRY(cudaStreamSynchronize(stream));      // an earlier launch may still read the old queues
+  CUDA_TRY(cudaStreamSynchronize(d.stream));
+  size_t ask = want;
+  for (;;) {
+    if (d.d_workspace) { cudaFree(d.d_workspace); d.d_workspace = nullptr; d.workspace_bytes = 0; }
+    if (cudaMalloc(&d.d_workspace, ask) == cudaSuccess) { d.workspace_bytes = ask; break; }
+    cudaGetLastError();                          // clear the allocation failure
+    d.d_workspace = nullptr;
+    d.workspace_denied = ask;
+    if (ask <= floor_bytes) return fail("render: cannot allocate %zu bytes of path queues", ask);
+    ask = ask / 2 > floor_bytes ? ask / 2 : floor_bytes;
+  }
   return 0;
 }
 
-int grow_pinned(size_t want);
+struct Share {            // what one device (or process) renders of a frame
+  isize s_begin, s_end;
+  int   split_rank, split_world;
+};
 
-// Host-side staging copy, split over a few threads above 4 MB: one core copies ~10 GB/s, and the 50 MB of
-// the helmet's textures staged per upload would otherwise cost more than their PCIe transfer.
-void staged_copy(void *dst, const void *src, size_t n) {
-  const size_t kMin = 4u << 20;
-  if (n < kMin) { memcpy(dst, src, n); return; }
-  const int parts = 4;
-  std::thread workers[parts - 1];
-  const size_t step = ((n / parts) + 63) & ~(size_t)63;
-  for (int i = 1; i < parts; i++) {
-    const size_t off = step * i, len = off < n ? (off + step < n && i + 1 < parts ? step : n - off) : 0;
-    workers[i - 1] = std::thread([=] { if (len) memcpy(static_cast<char *>(dst) + off, static_cast<const char *>(src) + off, len); });
-  }
-  memcpy(dst, src, step < n ? step : n);
-  for (auto &t : workers) t.join();
-}
-
-// host -> device through the pinned staging buffer, asynchronously on the library's stream;
-// staging is reused, so the copy of one buffer is drained before the next one is staged
-int upload_bytes(DeviceScene &ds, const void *host, size_t n, const void **out) {
-  void *p = nullptr;
-  const size_t alloc = n ? n : 16;
-  if (pool_alloc(&p, alloc)) return 1;
-  ds.allocations.push_back({p, alloc});
-  ds.bytes += n;
-  if (n) {
-    if (grow_pinned(n)) return 1;
-    CUDA_TRY(cudaStreamSynchronize(g.stream));
-    staged_copy(g.h_pinned, host, n);
-    ds.h2d_bytes += n;
-    CUDA_TRY(cudaMemcpyAsync(p, g.h_pinned, n, cudaMemcpyHostToDevice, g.stream));
-  }
-  *out = p;
-  return 0;
-}
-
-template <typename T>
-int upload(DeviceScene &ds, const std::vector<T> &host, const T **out) {
-  const void *p = nullptr;
-  if (upload_bytes(ds, host.data(), host.size() * sizeof(T), &p)) return 1;
-  *out = static_cast<const T *>(p);
-  return 0;
-}
-
-void release(DeviceScene &ds) {
-  for (auto &a : ds.allocations) g_block_pool.emplace(a.second, a.first);
-  ds.allocations.clear();
-}
-
-void drop_block_pool() {
-  for (auto &kv : g_block_pool) cudaFree(kv.second);
-  g_block_pool.clear();
-}
-
-int grow(void **ptr, size_t *have, size_t want) {
-  if (*have >= want && *ptr) return 0;
-  if (*ptr) cudaFree(*ptr);
-  *ptr = nullptr;
-  *have = 0;
-  CUDA_TRY(cudaMalloc(ptr, want));
-  *have = want;
-  return 0;
-}
-
-int grow_pinned(size_t want) {
-  if (g.pinned_bytes >= want && g.h_pinned) return 0;
-  if (g.h_pinned) cudaFreeHost(g.h_pinned);
-  g.h_pinned = nullptr;
-  g.pinned_bytes = 0;
-  CUDA_TRY(cudaMallocHost(reinterpret_cast<void **>(&g.h_pinned), want));
-  g.pinned_bytes = want;
-  return 0;
-}
-
-int build_device_scene(const Scene *scene, DeviceScene &ds) {
-  const isize depth = scene->bvh.depth;
-  if (depth < 1 || depth > RT_MAX_DEPTH) return fail("scene: BVH depth %ld outside [1,%d]", (long)depth, RT_MAX_DEPTH);
-  const isize n_nodes = scene->bvh.nodes.len, n_slots = scene->triangles.len;
-  if (n_nodes != bvh_n_internal_nodes(depth) || n_slots != bvh_n_leaf_nodes(depth) * RT_SIMD_WIDTH)
-    return fail("scene: node/slot counts do not describe a complete 8-ary tree of depth %ld", (long)depth);
-
-  std::vector<float> nodes((size_t)n_nodes * 48);
-  memcpy(nodes.data(), scene->bvh.nodes.data, nodes.size() * sizeof(float));
-
-  // per slot: p0.xyz, e1 = p1 - p0, e2 = p2 - p0.  The two edge vectors are the f32
-  // subtractions the reference redoes for every ray (raytracer.c:116-122); volatile keeps the
-  // host compiler from doing them in any wider type
-  std::vector<float4> tri_pos((size_t)n_slots * 3);
-  const float *px[3] = { scene->triangles.x[0], scene->triangles.y[0], scene->triangles.z[0] };
-  const float *p1[3] = { scene->triangles.x[1], scene->triangles.y[1], scene->triangles.z[1] };
-  const float *p2[3] = { scene->triangles.x[2], scene->triangles.y[2], scene->triangles.z[2] };
-  for (isize s = 0; s < n_slots; s++) {
-    volatile float e1[3], e2[3];
-    for (int a = 0; a < 3; a++) { e1[a] = p1[a][s] - px[a][s]; e2[a] = p2[a][s] - px[a][s]; }
-    tri_pos[(size_t)s * 3 + 0] = make_float4(px[0][s], px[1][s], px[2][s], e1[0]);
-    tri_pos[(size_t)s * 3 + 1] = make_float4(e1[1], e1[2], e2[0], e2[1]);
-    tri_pos[(size_t)s * 3 + 2] = make_float4(e2[2], 0.0f, 0.0f, 0.0f);
-  }
-
-  // materials / textures, de-duplicated by host pointer
-  std::map<const void *, int> material_index, texture_index;
-  std::vector<MaterialDev> materials;
-  std::vector<const Image *> images;
-  auto texture_slot = [&](const Image *im) -> int {
-    if (!im) return -1;
-    auto it = texture_index.find(im);
-    if (it != texture_index.end()) return it->second;
-    int slot = (int)images.size();
-    images.push_back(im);
-    texture_index[im] = slot;
-    return slot;
-  };
-
-  std::vector<float4> records((size_t)n_slots * 7);
-  for (isize s = 0; s < n_slots; s++) {
-    const Triangle_AOS &a = scene->triangles.aos[s];
-    int mat = 0;
-    if (a.shader.proc || a.shader.data) {
-      bool known = false;
-      for (Shader_Proc p : g.pbr_procs) known |= (p == a.shader.proc);
-      if (!known) return fail("scene: triangle slot %ld uses a Shader_Proc that was not registered with rt_gpu_register_pbr_shader", (long)s);
-      auto it = material_index.find(a.shader.data);
-      if (it == material_index.end()) {
-        const PBR_Shader_Data *m = static_cast<const PBR_Shader_Data *>(a.shader.data);
-        MaterialDev d{};
-        for (int c = 0; c < 3; c++) { d.base[c] = m->base_color.data[c]; d.emission[c] = m->emission.data[c]; }
-        d.roughness = m->roughness; d.metalness = m->metalness; d.normal_strength = m->normal_map_strength;
-        d.sheen = m->sheen; d.sheen_tint = m->sheen_tint; d.aniso = m->anisotropic_strength;
-        d.tex_albedo = texture_slot(m->texture_albedo);
-        d.tex_normal = texture_slot(m->texture_normal);
-        d.tex_mr = texture_slot(m->texture_metal_roughness);
-        d.tex_emission = texture_slot(m->texture_emission);
-        mat = (int)materials.size();
-        materials.push_back(d);
-        material_index[a.shader.data] = mat;
-      } else {
-        mat = it->second;
-      }
-    }
-    float4 *r = &records[(size_t)s * 7];
-    r[0] = make_float4(a.normal.x, a.normal.y, a.normal.z, a.normal_a.x);
-    r[1] = make_float4(a.normal_a.y, a.normal_a.z, a.normal_b.x, a.normal_b.y);
-    r[2] = make_float4(a.normal_b.z, a.normal_c.x, a.normal_c.y, a.normal_c.z);
-    r[3] = make_float4(a.tangent.x, a.tangent.y, a.tangent.z, a.bitangent.x);
-    r[4] = make_float4(a.bitangent.y, a.bitangent.z, a.tex_coords_a.x, a.tex_coords_a.y);
-    r[5] = make_float4(a.tex_coords_b.x, a.tex_coords_b.y, a.tex_coords_c.x, a.tex_coords_c.y);
-    int bits = mat;
-    float as_float;
-    memcpy(&as_float, &bits, 4);
-    r[6] = make_float4(as_float, 0, 0, 0);
-  }
-  if (materials.empty()) materials.push_back(MaterialDev{});
-
-  // environment
-  bool bg_known = false;
-  for (Background_Proc p : g.bg_procs) bg_known |= (p == scene->background.proc);
-  if (!bg_known || !scene->background.data)
-    return fail("scene: Scene.background.proc was not registered with rt_gpu_register_background (or its Image is null)");
-  int env_slot = texture_slot(static_cast<const Image *>(scene->background.data));
-
-  std::vector<TextureDev> textures(images.size());
-  for (size_t i = 0; i < images.size(); i++) {
-    const Image *im = images[i];
-    if (im->components < 3 || !im->pixels.data) return fail("scene: texture %zu needs >= 3 u8 components", i);
-    // raw texel bytes go up as they are (3 B per texel for RGB8); the RGBA8 repack the samplers read
-    // (one 32-bit load per tap) is done by a kernel on the device
-    const size_t n_texels = (size_t)im->width * (size_t)im->height;
-    const size_t raw_bytes = (size_t)im->stride * (size_t)im->height * (size_t)im->components;
-    void *d_texels_raw = nullptr;
-    if (pool_alloc(&d_texels_raw, n_texels * sizeof(uchar4))) return 1;
-    ds.allocations.push_back({d_texels_raw, n_texels * sizeof(uchar4)});
-    ds.bytes += n_texels * sizeof(uchar4);
-    size_t have = g.texel_stage_bytes;
-    if (grow(&g.d_texel_stage, &have, raw_bytes)) return 1;
-    g.texel_stage_bytes = have;
-    if (grow_pinned(raw_bytes)) return 1;
-    CUDA_TRY(cudaStreamSynchronize(g.stream));
-    staged_copy(g.h_pinned, im->pixels.data, raw_bytes);
-    ds.h2d_bytes += raw_bytes;
-    CUDA_TRY(cudaMemcpyAsync(g.d_texel_stage, g.h_pinned, raw_bytes, cudaMemcpyHostToDevice, g.stream));
-    int e = rt_launch_texel_repack(static_cast<const unsigned char *>(g.d_texel_stage), (int)im->width, (int)im->height,
-                                   (int)im->stride, im->components, static_cast<uchar4 *>(d_texels_raw), g.stream);
-    if (e) return fail("texel repack launch failed: %s", cudaGetErrorString((cudaError_t)e));
-    const uchar4 *d_texels = static_cast<const uchar4 *>(d_texels_raw);
-    textures[i].texels = d_texels;
-    textures[i].width = (int)im->width;
-    textures[i].height = (int)im->height;
-  }
-
-  SceneDev &dev = ds.dev;
-  if (upload(ds, nodes, &dev.nodes)) return 1;
-  if (upload(ds, tri_pos, &dev.tri_pos)) return 1;
-  if (upload(ds, records, &dev.tri_rec)) return 1;
-  {
-    // camera-relative copies for the primary trace, filled by rt_camera_relative_kernel at every render
-    void *p = nullptr;
-    const size_t node_bytes = nodes.size() * sizeof(float), tri_bytes = (size_t)n_slots * 4 * sizeof(float4);
-    if (pool_alloc(&p, node_bytes)) return 1;
-    ds.allocations.push_back({p, node_bytes}); ds.bytes += node_bytes;
-    dev.nodes_rel = static_cast<float *>(p);
-    if (pool_alloc(&p, tri_bytes)) return 1;
-    ds.allocations.push_back({p, tri_bytes}); ds.bytes += tri_bytes;
-    dev.tri_rel = static_cast<float4 *>(p);
-  }
-  if (upload(ds, materials, &dev.materials)) return 1;
-  if (upload(ds, textures, &dev.textures)) return 1;
-  dev.env_texture = env_slot;
-  dev.depth = (int)depth;
-  dev.n_internal = (int)n_nodes;
-  dev.n_slots = (int)n_slots;
-  // union of the root's child boxes; all-zero padding slots (lo == hi) can never be entered
-  // (enter >= leave) and are left out
-  for (int a = 0; a < 3; a++) { dev.root_lo[a] = INFINITY; dev.root_hi[a] = -INFINITY; }
-  for (int j = 0; j < 8; j++) {
-    const float *n0 = nodes.data();
-    bool empty = true;
-    for (int a = 0; a < 3; a++) empty &= (n0[a * 8 + j] == n0[(3 + a) * 8 + j]);
-    if (empty) continue;
-    for (int a = 0; a < 3; a++) {
-      dev.root_lo[a] = fminf(dev.root_lo[a], n0[a * 8 + j]);
-      dev.root_hi[a] = fmaxf(dev.root_hi[a], n0[(3 + a) * 8 + j]);
-    }
-  }
-  // renders may run on another stream (device-pointer level): the scene is complete when this returns
-  CUDA_TRY(cudaStreamSynchronize(g.stream));
-  return 0;
-}
-
-void refresh_camera(const Scene *scene, SceneDev &dev) {
-  for (int r = 0; r < 3; r++)
-    for (int c = 0; c < 4; c++) dev.view[r][c] = scene->camera.view_matrix.rows[r][c];
-  dev.focal_length = scene->camera.focal_length;
-}
-
-int scene_on_device(const Scene *scene, SceneDev *out) {
-  auto it = g.scenes.find(scene);
-  if (it == g.scenes.end()) {
-    DeviceScene ds;
-    if (build_device_scene(scene, ds)) { release(ds); return 1; }
-    it = g.scenes.emplace(scene, std::move(ds)).first;
-  }
-  refresh_camera(scene, it->second.dev);      // the camera is cheap and may change between frames
-  *out = it->second.dev;
-  return 0;
-}
-
-int render_device_locked(const Scene *scene, isize width, isize height, isize s_begin, isize s_end, isize max_bounces,
-                         u32 seed, int accumulate, float *d_accum, float *d_per_sample, int *d_hit_ids,
-                         unsigned long long *d_counters, cudaStream_t stream) {
+// One render of `share` on device d, enqueued on `stream`.  Every render of a device uses the device's one workspace
+// and rewrites the scene's camera-relative copies, so renders are serialised on the device whatever stream they come
+// from: each waits for the event the previous one recorded.
+int render_on_device(Device &d, const Scene *scene, isize width, isize height, const Share &share, isize max_bounces,
+                     u32 seed, int accumulate, float *d_accum, float *d_per_sample, int *d_hit_ids,
+                     unsigned long long *d_counters, cudaStream_t stream) {
   if (width < 1 || height < 1) return fail("render: empty image");
+  CUDA_TRY(cudaSetDevice(d.id));
+  auto it = d.scenes.find(scene);
+  if (it == d.scenes.end()) return fail("render: scene is not resident on device %d", d.id);
+  const DeviceScene &ds = it->second;
   RenderParams p{};
-  if (scene_on_device(scene, &p.scene)) return 1;
-  const size_t want = rt_render_workspace_bytes((int)width, (int)height, (int)(s_end - s_begin), (int)max_bounces,
-                                                g.options.slice_samples);
-  if (g.workspace_bytes < want) {
-    CUDA_TRY(cudaStreamSynchronize(stream));      // an earlier launch may still read the old queues
-    // the preferred size (up to 26.6 GB) is a throughput choice, not a requirement: on a device that
-    // cannot spare it, halve the request down to one sample of every pixel per chunk
-    const size_t floor_bytes = rt_render_workspace_bytes((int)width, (int)height, 1, (int)max_bounces, 1);
-    size_t ask = want;
-    for (;;) {
-      if (g.d_workspace) { cudaFree(g.d_workspace); g.d_workspace = nullptr; g.workspace_bytes = 0; }
-      if (cudaMalloc(&g.d_workspace, ask) == cudaSuccess) { g.workspace_bytes = ask; break; }
-      cudaGetLastError();                          // clear the allocation failure
-      g.d_workspace = nullptr;
-      if (ask <= floor_bytes) return fail("render: cannot allocate %zu bytes of path queues", ask);
-      ask = ask / 2 > floor_bytes ? ask / 2 : floor_bytes;
-    }
-  }
+  p.scene = ds.dev;
+  const int n_samples = (int)(share.s_end - share.s_begin);
+  const size_t want = rt_render_workspace_bytes((int)width, (int)height, n_samples, (int)max_bounces,
+                                                g.options.slice_samples, share.split_world);
+  const size_t floor_bytes = rt_render_workspace_bytes((int)width, (int)height, 1, (int)max_bounces, 1, share.split_world);
+  if (n_samples > 0 && ensure_workspace(d, want, floor_bytes, stream)) return 1;
+  if (d.busy_valid) CUDA_TRY(cudaStreamWaitEvent(stream, d.busy, 0));
+  CUDA_TRY(cudaStreamWaitEvent(stream, ds.geom_ready, 0));
+  p.shading_ready = ds.tex_ready;
+  set_l2_window(d, ds, stream);
   p.width = (int)width; p.height = (int)height;
-  p.sample_begin = (int)s_begin; p.sample_end = (int)s_end; p.max_bounces = (int)max_bounces;
+  p.split_rank = share.split_rank; p.split_world = share.split_world;
+  p.sample_begin = (int)share.s_begin; p.sample_end = (int)share.s_end; p.max_bounces = (int)max_bounces;
   p.user_seed = seed;
   p.accumulate = accumulate;
   p.accum = d_accum; p.per_sample = d_per_sample; p.hit_ids = d_hit_ids;
   p.counters = d_counters;
-  int e = rt_launch_render(p, g.sm_count, g.d_workspace, g.workspace_bytes, stream, &g.last_launches);
+  p.counters_ex = (d_counters && d_counters == d.d_counters) ? d_counters + 8 : nullptr;   // the library's own buffer has 16 slots
+  int e = rt_launch_render(p, d.sm_count, d.d_workspace, d.workspace_bytes, stream, &g.last_launches);
   if (e) return fail("render kernel launch failed: %s", cudaGetErrorString((cudaError_t)e));
+  CUDA_TRY(cudaEventRecord(d.busy, stream));
+  d.busy_valid = true;
+  return 0;
+}
+
+int ensure_frame_buffers(Device &d, size_t n_pixels, bool hit_ids) {
+  CUDA_TRY(cudaSetDevice(d.id));
+  size_t have = d.accum_floats * sizeof(float);
+  if (grow(reinterpret_cast<void **>(&d.d_accum), &have, n_pixels * 3 * sizeof(float))) return 1;
+  d.accum_floats = have / sizeof(float);
+  if (hit_ids) {
+    have = d.hit_pixels * sizeof(int);
+    if (grow(reinterpret_cast<void **>(&d.d_hit_ids), &have, n_pixels * sizeof(int))) return 1;
+    d.hit_pixels = have / sizeof(int);
+  }
+  if (!d.d_counters) CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&d.d_counters), 16 * sizeof(unsigned long long)));
   return 0;
 }
 
@@ -384,36 +198,27 @@ extern "C" {
 
 int rt_gpu_init(int device) {
   std::lock_guard<std::mutex> lock(g_mutex);
-  if (g.ready && g.device == device) return 0;
+  return init_devices_locked(1, &device);
+}
+
+int rt_gpu_init_devices(int n_devices, int const *devices) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  return init_devices_locked(n_devices, devices);
+}
+
+int rt_gpu_device_count(void) { return g.ready ? (int)g.devs.size() : 0; }
+
+int rt_gpu_visible_devices(void) {
   int count = 0;
-  cudaError_t e = cudaGetDeviceCount(&count);
-  if (e != cudaSuccess || count == 0)
-    return fail("no CUDA device available (%s); libraytracer_gpu has no CPU fallback", cudaGetErrorString(e));
-  if (device < 0 || device >= count) return fail("device %d out of range (%d visible)", device, count);
-  CUDA_TRY(cudaSetDevice(device));
-  cudaDeviceProp prop;
-  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
-  if (prop.major < 10) return fail("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
-  g.device = device;
-  g.sm_count = prop.multiProcessorCount;
-  if (!g.stream) CUDA_TRY(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
-  if (!g.ev0) CUDA_TRY(cudaEventCreate(&g.ev0));
-  if (!g.ev1) CUDA_TRY(cudaEventCreate(&g.ev1));
-  g.ready = true;
-  return 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return count;
 }
 
 void rt_gpu_shutdown(void) {
   std::lock_guard<std::mutex> lock(g_mutex);
-  for (auto &kv : g.scenes) release(kv.second);
-  g.scenes.clear();
-  cudaFree(g.d_accum); cudaFree(g.d_hit_ids); cudaFree(g.d_counters); cudaFree(g.d_workspace); cudaFree(g.d_texel_stage);
-  drop_block_pool();
-  cudaFree(g.d_image); cudaFree(g.d_image2);
-  if (g.h_pinned) cudaFreeHost(g.h_pinned);
-  if (g.ev0) cudaEventDestroy(g.ev0);
-  if (g.ev1) cudaEventDestroy(g.ev1);
-  if (g.stream) cudaStreamDestroy(g.stream);
+  nccl_shutdown();
+  ipc_close_all();
+  for (Device &d : g.devs) release_device(d);
   std::vector<Shader_Proc> pbr = g.pbr_procs;
   std::vector<Background_Proc> bg = g.bg_procs;
   g = State{};
@@ -421,26 +226,41 @@ void rt_gpu_shutdown(void) {
   g.bg_procs = bg;
 }
 
-char const *rt_gpu_last_error(void) { return g_error[0] ? g_error : g_error_shared; }
+char const *rt_gpu_last_error(void) {
+  std::lock_guard<std::mutex> lock(g_error_mutex);
+  memcpy(g_error_copy, g_error_shared, sizeof g_error_copy);
+  return g_error_copy;
+}
 
-int rt_gpu_sm_count(void) { return ensure_init() ? 0 : g.sm_count; }
+int rt_gpu_last_status(void) { return g_status.load(); }
+
+int rt_gpu_sm_count(void) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  return ensure_init() ? 0 : g.devs[0].sm_count;
+}
 
 f64 rt_gpu_measure_fp32_issue(void) {
-  if (ensure_init()) return 0;
   std::lock_guard<std::mutex> lock(g_mutex);
-  return rt_measure_fp32_issue(g.sm_count, g.stream, nullptr);
+  if (ensure_init()) return 0;
+  cudaSetDevice(g.devs[0].id);
+  return rt_measure_fp32_issue(g.devs[0].sm_count, g.devs[0].stream, nullptr);
 }
 
 isize rt_gpu_scene_device_bytes(Scene const *scene) {
   std::lock_guard<std::mutex> lock(g_mutex);
-  auto it = g.scenes.find(scene);
-  return it == g.scenes.end() ? 0 : (isize)it->second.bytes;
+  if (g.devs.empty()) return 0;
+  auto it = g.devs[0].scenes.find(scene);
+  return it == g.devs[0].scenes.end() ? 0 : (isize)it->second.bytes;
 }
 
 isize rt_gpu_scene_upload_bytes(Scene const *scene) {
   std::lock_guard<std::mutex> lock(g_mutex);
-  auto it = g.scenes.find(scene);
-  return it == g.scenes.end() ? 0 : (isize)it->second.h2d_bytes;
+  isize total = 0;
+  for (Device &d : g.devs) {
+    auto it = d.scenes.find(scene);
+    if (it != d.scenes.end()) total += (isize)it->second.h2d_bytes;
+  }
+  return total;
 }
 
 void rt_gpu_register_pbr_shader(Shader_Proc proc) {
@@ -466,25 +286,29 @@ Color3 rt_gpu_background_proc(rawptr, Vec3) {
 }
 
 int rt_gpu_scene_upload(Scene const *scene) {
-  if (ensure_init()) return 1;
   std::lock_guard<std::mutex> lock(g_mutex);
-  auto it = g.scenes.find(scene);
-  if (it != g.scenes.end()) {
-    cudaDeviceSynchronize();          // its blocks are reused below: no render may still read them
-    release(it->second);
-    g.scenes.erase(it);
-  }
-  SceneDev dev;
-  return scene_on_device(scene, &dev);
+  if (ensure_init()) return 1;
+  if (g.devs.size() > 1 && enable_peers()) return 1;
+  return scene_upload_all(scene);
 }
 
 void rt_gpu_scene_release(Scene const *scene) {
   std::lock_guard<std::mutex> lock(g_mutex);
-  auto it = g.scenes.find(scene);
-  if (it == g.scenes.end()) return;
-  cudaDeviceSynchronize();
-  release(it->second);
-  g.scenes.erase(it);
+  scene_release_all(scene);
+}
+
+void *rt_gpu_host_alloc(size_t bytes) {
+  void *p = nullptr;
+  // portable: pinned for every device this process drives, not only the current one
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
+    fail("rt_gpu_host_alloc(%zu): %s", bytes, cudaGetErrorString(cudaGetLastError()));
+    return nullptr;
+  }
+  return p;
+}
+
+void rt_gpu_host_free(void *p) {
+  if (p) cudaFreeHost(p);
 }
 
 void rt_gpu_set_options(RT_GPU_Options const *options) {
@@ -496,22 +320,67 @@ void rt_gpu_set_options(RT_GPU_Options const *options) {
 void rt_gpu_get_options(RT_GPU_Options *options) {
   std::lock_guard<std::mutex> lock(g_mutex);
   *options = g.options;
+  if (options->slice_samples < 1) options->slice_samples = 64;
 }
 
 // ------------------------------------------------------------ device-pointer level
 int rt_gpu_render_accum_device(Scene const *scene, isize width, isize height, isize sample_begin, isize sample_end,
                                isize max_bounces, u32 user_seed, i32 accumulate, f32 *d_accum, f32 *d_per_sample,
                                i32 *d_hit_ids, u64 *d_counters, void *stream) {
-  if (ensure_init()) return 1;
   std::lock_guard<std::mutex> lock(g_mutex);
-  return render_device_locked(scene, width, height, sample_begin, sample_end, max_bounces, user_seed, accumulate,
-                              d_accum, d_per_sample, d_hit_ids, reinterpret_cast<unsigned long long *>(d_counters),
-                              static_cast<cudaStream_t>(stream));
+  if (ensure_init()) return 1;
+  if (scene_on_devices(scene)) return 1;
+  const Share share{sample_begin, sample_end, g.options.pixel_rank, g.options.pixel_world};
+  return render_on_device(g.devs[0], scene, width, height, share, max_bounces, user_seed, accumulate, d_accum, d_per_sample,
+                          d_hit_ids, reinterpret_cast<unsigned long long *>(d_counters), static_cast<cudaStream_t>(stream));
+}
+
+int rt_gpu_render_shard_device(Scene const *scene, isize width, isize height, isize samples, isize max_bounces,
+                               u32 user_seed, i32 rank, i32 world, i32 split_mode, i32 *mode_used,
+                               f32 *d_accum, u64 *d_counters, void *stream) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  if (ensure_init()) return 1;
+  if (world < 1 || rank < 0 || rank >= world) return fail("render_shard: rank %d of %d", rank, world);
+  if (scene_on_devices(scene)) return 1;
+  const i32 mode = rt_gpu_shard_mode((i32)samples, world, split_mode);
+  if (mode_used) *mode_used = mode;
+  Share share{0, samples, 0, 1};
+  if (mode == RT_GPU_SPLIT_SAMPLES) {
+    i32 a = 0, b = 0;
+    rt_gpu_shard_samples(rank, world, (i32)samples, &a, &b);
+    share.s_begin = a; share.s_end = b;
+  } else {
+    share.split_rank = rank; share.split_world = world;
+  }
+  return render_on_device(g.devs[0], scene, width, height, share, max_bounces, user_seed, 0, d_accum, nullptr, nullptr,
+                          reinterpret_cast<unsigned long long *>(d_counters), static_cast<cudaStream_t>(stream));
+}
+
+int rt_gpu_accum_buffer(isize width, isize height, f32 **d_accum_out) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  if (ensure_init()) return 1;
+  if (width < 1 || height < 1) return fail("accum_buffer: empty image");
+  if (ensure_frame_buffers(g.devs[0], (size_t)width * (size_t)height, false)) return 1;
+  *d_accum_out = g.devs[0].d_accum;
+  return 0;
+}
+
+int rt_gpu_reduce_resolve_device(f32 const *const *d_parts, i32 n_parts, f32 *d_sum_out, isize width, isize height,
+                                 isize samples, u8 *d_pixels, isize stride, i32 components, void *stream) {
+  if (n_parts < 1 || n_parts > RT_MAX_PARTS) return fail("reduce_resolve: between 1 and %d parts", RT_MAX_PARTS);
+  if (samples < 1 || (d_pixels && components < 3)) return fail("reduce_resolve: samples >= 1 and components >= 3 required");
+  ReduceParts parts{};
+  parts.n = n_parts;
+  for (int k = 0; k < n_parts; k++) parts.part[k] = d_parts[k];
+  int e = rt_launch_reduce_resolve(parts, d_sum_out, (int)width, (int)height, (int)samples, d_pixels, (int)stride, components,
+                                   static_cast<cudaStream_t>(stream));
+  if (e) return fail("reduce+resolve kernel launch failed: %s", cudaGetErrorString((cudaError_t)e));
+  g.last_launches++;
+  return 0;
 }
 
 int rt_gpu_resolve_device(f32 const *d_accum, isize width, isize height, isize samples, u8 *d_pixels, isize stride,
                           i32 components, void *stream) {
-  if (ensure_init()) return 1;
   if (samples < 1 || components < 3) return fail("resolve: samples >= 1 and components >= 3 required");
   int e = rt_launch_resolve(d_accum, (int)width, (int)height, (int)samples, d_pixels, (int)stride, components,
                             static_cast<cudaStream_t>(stream));
@@ -522,7 +391,6 @@ int rt_gpu_resolve_device(f32 const *d_accum, isize width, isize height, isize s
 
 int rt_gpu_denoise_device(u8 const *d_src, u8 *d_dst, isize width, isize height, isize src_stride, isize dst_stride,
                           i32 components, void *stream) {
-  if (ensure_init()) return 1;
   if (d_src == d_dst) return fail("denoise: src and dst must differ (reference denoiser.c:130)");
   int e = rt_launch_denoise(d_src, d_dst, (int)width, (int)height, (int)src_stride, (int)dst_stride, components,
                             static_cast<cudaStream_t>(stream));
@@ -534,23 +402,84 @@ int rt_gpu_denoise_device(u8 const *d_src, u8 *d_dst, isize width, isize height,
 // ----------------------------------------------------------------- parity hooks
 int rt_gpu_read_accum(f32 *out, isize n_floats) {
   std::lock_guard<std::mutex> lock(g_mutex);
-  if (!g.d_accum || (size_t)n_floats > g.last_pixels * 3) return fail("read_accum: no render of that size has run");
-  CUDA_TRY(cudaMemcpy(out, g.d_accum, (size_t)n_floats * sizeof(float), cudaMemcpyDeviceToHost));
+  if (g.devs.empty() || !g.devs[0].d_accum || (size_t)n_floats > g.last_pixels * 3) return fail("read_accum: no render of that size has run");
+  CUDA_TRY(cudaSetDevice(g.devs[0].id));
+  CUDA_TRY(cudaMemcpy(out, g.devs[0].d_accum, (size_t)n_floats * sizeof(float), cudaMemcpyDeviceToHost));
   return 0;
 }
 
 int rt_gpu_read_hit_ids(i32 *out, isize n_pixels) {
   std::lock_guard<std::mutex> lock(g_mutex);
-  if (!g.d_hit_ids || !g.last_has_hit_ids || (size_t)n_pixels > g.last_pixels)
+  if (g.devs.empty() || !g.devs[0].d_hit_ids || !g.last_has_hit_ids || (size_t)n_pixels > g.last_pixels)
     return fail("read_hit_ids: the last render did not keep hit ids (RT_GPU_Options.keep_hit_ids)");
-  CUDA_TRY(cudaMemcpy(out, g.d_hit_ids, (size_t)n_pixels * sizeof(int), cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaSetDevice(g.devs[0].id));
+  CUDA_TRY(cudaMemcpy(out, g.devs[0].d_hit_ids, (size_t)n_pixels * sizeof(int), cudaMemcpyDeviceToHost));
+  if (g.last_split_mode == RT_GPU_SPLIT_CHUNKS && g.devs.size() > 1) {
+    // chunk split: every device recorded the pixels of its own chunks, INT_MIN elsewhere
+    std::vector<int> other((size_t)n_pixels);
+    for (size_t k = 1; k < g.devs.size(); k++) {
+      CUDA_TRY(cudaSetDevice(g.devs[k].id));
+      CUDA_TRY(cudaMemcpy(other.data(), g.devs[k].d_hit_ids, (size_t)n_pixels * sizeof(int), cudaMemcpyDeviceToHost));
+      for (isize i = 0; i < n_pixels; i++) if (other[(size_t)i] > out[i]) out[i] = other[(size_t)i];
+    }
+    CUDA_TRY(cudaSetDevice(g.devs[0].id));
+  }
   return 0;
 }
 
 int rt_gpu_read_counters(u64 out[8]) {
   std::lock_guard<std::mutex> lock(g_mutex);
-  if (!g.d_counters) return fail("read_counters: no render has run");
-  CUDA_TRY(cudaMemcpy(out, g.d_counters, 8 * sizeof(u64), cudaMemcpyDeviceToHost));
+  if (g.devs.empty() || !g.devs[0].d_counters) return fail("read_counters: no render has run");
+  for (int i = 0; i < 8; i++) out[i] = 0;
+  for (Device &d : g.devs) {
+    if (!d.d_counters) continue;
+    u64 part[8];
+    CUDA_TRY(cudaSetDevice(d.id));
+    CUDA_TRY(cudaMemcpy(part, d.d_counters, sizeof part, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 8; i++) out[i] += part[i];
+  }
+  CUDA_TRY(cudaSetDevice(g.devs[0].id));
+  return 0;
+}
+
+// The library's own 16-slot counter block on the first device: [0..8) as RT_GPU_CTR_*, [8] rays whose whole walk
+// was the root-union test (they count as one node visit in [1], as in the reference, but cost 18 instructions),
+// [9] primary rays.  Pass it as d_counters to the device-level calls to have the extended slots filled.
+int rt_gpu_counters_buffer(u64 **d_counters_out) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  if (ensure_init()) return 1;
+  Device &d = g.devs[0];
+  CUDA_TRY(cudaSetDevice(d.id));
+  if (!d.d_counters) {
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&d.d_counters), 16 * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemset(d.d_counters, 0, 16 * sizeof(unsigned long long)));
+  }
+  *d_counters_out = reinterpret_cast<u64 *>(d.d_counters);
+  return 0;
+}
+
+int rt_gpu_counters_reset(void) {
+  u64 *p = nullptr;
+  if (rt_gpu_counters_buffer(&p)) return 1;
+  std::lock_guard<std::mutex> lock(g_mutex);
+  CUDA_TRY(cudaSetDevice(g.devs[0].id));
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemset(p, 0, 16 * sizeof(u64)));
+  return 0;
+}
+
+int rt_gpu_read_counters_ex(u64 out[16]) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  if (g.devs.empty() || !g.devs[0].d_counters) return fail("read_counters: no render has run");
+  for (int i = 0; i < 16; i++) out[i] = 0;
+  for (Device &d : g.devs) {
+    if (!d.d_counters) continue;
+    u64 part[16];
+    CUDA_TRY(cudaSetDevice(d.id));
+    CUDA_TRY(cudaMemcpy(part, d.d_counters, sizeof part, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 16; i++) out[i] += part[i];
+  }
+  CUDA_TRY(cudaSetDevice(g.devs[0].id));
   return 0;
 }
 
@@ -558,7 +487,7 @@ int rt_gpu_last_launches(void) { return g.last_launches; }
 
 void rt_gpu_stage_profile_enable(i32 on) {
   std::lock_guard<std::mutex> lock(g_mutex);
-  rt_stage_profile_enable(on);
+  rt_stage_profile_enable(on, g.devs.empty() ? 0 : g.devs[0].id);
 }
 
 int rt_gpu_stage_profile_read_bounces(f64 ms[64], i64 launches[64]) {
@@ -583,69 +512,167 @@ int rt_gpu_stage_profile_read(f64 ms[4], i64 launches[4]) {
 
 f64 rt_gpu_last_kernel_ms(void) { return g.last_kernel_ms; }
 
+void rt_gpu_last_frame_breakdown(f64 out[4]) {
+  out[0] = g.last_upload_ms; out[1] = g.last_reduce_ms; out[2] = g.last_d2h_ms; out[3] = (f64)g.last_split_mode;
+}
+
 // ------------------------------------------------------- reference entry points
 static int render_owner(Rendering_Context *ctx, isize n_chunks) {
-  if (ensure_init()) return 1;
   std::lock_guard<std::mutex> lock(g_mutex);
+  g.last_launches = 0;
+  if (ensure_init()) return 1;
   const Image &im = ctx->image;
   if (im.components < 3 || im.pixel_type != PT_u8 || !im.pixels.data) return fail("render: image must be u8 with >= 3 components");
+  if (im.width < 1 || im.height < 1 || im.stride < im.width) return fail("render: empty image or stride < width");
   if (ctx->samples < 1) return fail("render: samples must be >= 1");
-  CUDA_TRY(cudaSetDevice(g.device));
+  if (!ctx->scene) return fail("render: null scene");
+  const size_t n_dev = g.devs.size();
+  if (n_dev > 1 && enable_peers()) return 1;
   const size_t n_pixels = (size_t)im.width * (size_t)im.height;
   const size_t image_bytes = (size_t)im.stride * (size_t)im.height * (size_t)im.components;
-
-  size_t have = g.accum_floats * sizeof(float);
-  if (grow(reinterpret_cast<void **>(&g.d_accum), &have, n_pixels * 3 * sizeof(float))) return 1;
-  g.accum_floats = have / sizeof(float);
-  have = g.hit_pixels * sizeof(int);
-  if (grow(reinterpret_cast<void **>(&g.d_hit_ids), &have, n_pixels * sizeof(int))) return 1;
-  g.hit_pixels = have / sizeof(int);
-  if (!g.d_counters) CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&g.d_counters), 8 * sizeof(unsigned long long)));
-  if (grow(reinterpret_cast<void **>(&g.d_image), &g.image_bytes, image_bytes)) return 1;
-  if (grow_pinned(image_bytes)) return 1;
-
   const RT_GPU_Options opt = g.options;
-  const isize s_begin = opt.sample_begin;
-  const isize s_end = opt.sample_end > 0 ? opt.sample_end : ctx->samples;
-  const isize slice = opt.slice_samples > 0 ? opt.slice_samples : 64;
 
-  g.last_launches = 0;
+  double t0 = now_ms();
+  bool was_resident = true;
+  for (Device &d : g.devs) was_resident &= d.scenes.find(ctx->scene) != d.scenes.end();
+  if (scene_on_devices(ctx->scene)) return 1;
+  g.last_upload_ms = was_resident ? 0.0 : now_ms() - t0;
+
+  for (Device &d : g.devs)
+    if (ensure_frame_buffers(d, n_pixels, opt.keep_hit_ids != 0)) return 1;
+  Device &d0 = g.devs[0];
+  CUDA_TRY(cudaSetDevice(d0.id));
+  if (grow(reinterpret_cast<void **>(&d0.d_image), &d0.image_bytes, image_bytes)) return 1;
+  if (grow_pinned(d0, image_bytes)) return 1;
+
+  // the samples this call renders (a multi-process host narrows them per rank), then their split over the devices
+  isize s_begin = opt.sample_begin, s_end = opt.sample_end;
+  if (!opt.sample_range_set && s_end <= 0) s_end = ctx->samples;
+  if (s_begin < 0) s_begin = 0;
+  if (s_end > ctx->samples) s_end = ctx->samples;
+  if (s_end < s_begin) s_end = s_begin;
+  const isize slice = opt.slice_samples > 0 ? opt.slice_samples : 64;
+  const i32 mode = n_dev > 1 ? rt_gpu_shard_mode((i32)(s_end - s_begin), (i32)n_dev, opt.split_mode) : RT_GPU_SPLIT_SAMPLES;
+
   g.last_pixels = n_pixels;
   g.last_has_hit_ids = opt.keep_hit_ids != 0;
-  CUDA_TRY(cudaMemsetAsync(g.d_counters, 0, 8 * sizeof(unsigned long long), g.stream));
+  g.last_split_mode = mode;
   // rows padded by stride keep whatever the caller had there
   if (im.stride != im.width || im.components != 3) {
-    memcpy(g.h_pinned, im.pixels.data, image_bytes);
-    CUDA_TRY(cudaMemcpyAsync(g.d_image, g.h_pinned, image_bytes, cudaMemcpyHostToDevice, g.stream));
+    memcpy(d0.h_pinned, im.pixels.data, image_bytes);
+    CUDA_TRY(cudaMemcpyAsync(d0.d_image, d0.h_pinned, image_bytes, cudaMemcpyHostToDevice, d0.stream));
   }
 
-  CUDA_TRY(cudaEventRecord(g.ev0, g.stream));
-  const isize n_slices = (s_end - s_begin + slice - 1) / slice;
-  for (isize k = 0; k < n_slices; k++) {
-    isize a = s_begin + k * slice, b = a + slice < s_end ? a + slice : s_end;
-    if (render_device_locked(ctx->scene, im.width, im.height, a, b, ctx->max_bounces, opt.user_seed, k > 0,
-                             g.d_accum, nullptr, (opt.keep_hit_ids && k == 0) ? g.d_hit_ids : nullptr,
-                             g.d_counters, g.stream))
-      return 1;
-    if (n_slices > 1 && (k % 4 == 3)) {
-      // progress for the host's bar (driver.c:810-818); never reaches n_chunks early
-      CUDA_TRY(cudaStreamSynchronize(g.stream));
-      isize progress = n_chunks * (k + 1) / n_slices;
+  CUDA_TRY(cudaEventRecord(d0.ev0, d0.stream));
+  std::vector<Share> shares(n_dev);
+  isize max_slices = 0;
+  for (size_t k = 0; k < n_dev; k++) {
+    Share &sh = shares[k];
+    sh = Share{s_begin, s_end, opt.pixel_rank, opt.pixel_world};
+    if (n_dev > 1) {
+      if (mode == RT_GPU_SPLIT_SAMPLES) {
+        i32 a = 0, b = 0;
+        rt_gpu_shard_samples((i32)k, (i32)n_dev, (i32)(s_end - s_begin), &a, &b);
+        sh.s_begin = s_begin + a; sh.s_end = s_begin + b;
+      } else {
+        sh.split_rank = (int)k; sh.split_world = (int)n_dev;
+      }
+    }
+    const isize n_slices = (sh.s_end - sh.s_begin + slice - 1) / slice;
+    if (n_slices > max_slices) max_slices = n_slices;
+  }
+  // slices round-robin over the devices, so the host's progress bar (driver.c:810-818) follows all of them
+  for (size_t k = 0; k < n_dev; k++) {
+    Device &d = g.devs[k];
+    CUDA_TRY(cudaSetDevice(d.id));
+    CUDA_TRY(cudaMemsetAsync(d.d_counters, 0, 16 * sizeof(unsigned long long), d.stream));
+    if (opt.keep_hit_ids && shares[k].split_world > 1)
+      CUDA_TRY(cudaMemsetAsync(d.d_hit_ids, 0x80, n_pixels * sizeof(int), d.stream));      // 0x80808080 < -1: "not mine"
+    if (shares[k].s_end <= shares[k].s_begin) {
+      // an empty share still defines its accumulator: zero
+      const Share empty{shares[k].s_begin, shares[k].s_begin, shares[k].split_rank, shares[k].split_world};
+      if (render_on_device(d, ctx->scene, im.width, im.height, empty, ctx->max_bounces, opt.user_seed, 0, d.d_accum,
+                           nullptr, nullptr, d.d_counters, d.stream))
+        return 1;
+    }
+  }
+  for (isize j = 0; j < max_slices; j++) {
+    for (size_t k = 0; k < n_dev; k++) {
+      const Share &sh = shares[k];
+      const isize a = sh.s_begin + j * slice;
+      if (a >= sh.s_end) continue;
+      const Share part{a, a + slice < sh.s_end ? a + slice : sh.s_end, sh.split_rank, sh.split_world};
+      Device &d = g.devs[k];
+      const bool first = j == 0;
+      if (render_on_device(d, ctx->scene, im.width, im.height, part, ctx->max_bounces, opt.user_seed, first ? 0 : 1, d.d_accum,
+                           nullptr, (opt.keep_hit_ids && first && (k == 0 || sh.split_world > 1)) ? d.d_hit_ids : nullptr,
+                           d.d_counters, d.stream))
+        return 1;
+    }
+    if (max_slices > 1 && (j % 4 == 3)) {
+      // progress for the host's bar; never reaches n_chunks early
+      for (Device &d : g.devs) { CUDA_TRY(cudaSetDevice(d.id)); CUDA_TRY(cudaStreamSynchronize(d.stream)); }
+      isize progress = n_chunks * (j + 1) / max_slices;
       if (progress >= n_chunks) progress = n_chunks - 1;
       if (progress > ctx->_current_chunk) ctx->_current_chunk = (i32)progress;
     }
   }
-  CUDA_TRY(cudaEventRecord(g.ev1, g.stream));
-  int e = rt_launch_resolve(g.d_accum, (int)im.width, (int)im.height, (int)ctx->samples, g.d_image, (int)im.stride,
-                            im.components, g.stream);
-  if (e) return fail("resolve kernel launch failed: %s", cudaGetErrorString((cudaError_t)e));
+  CUDA_TRY(cudaSetDevice(d0.id));
+  CUDA_TRY(cudaEventRecord(d0.ev1, d0.stream));
+
+  // ---- film: combine the devices' accumulators on the first one and resolve (raytracer.c:700-716)
+  cudaEvent_t r0 = nullptr, r1 = nullptr;
+  if (n_dev > 1) {
+    for (size_t k = 1; k < n_dev; k++) {
+      CUDA_TRY(cudaSetDevice(g.devs[k].id));
+      CUDA_TRY(cudaEventRecord(g.devs[k].done, g.devs[k].stream));
+    }
+    CUDA_TRY(cudaSetDevice(d0.id));
+    CUDA_TRY(cudaEventCreate(&r0));
+    CUDA_TRY(cudaEventCreate(&r1));
+    for (size_t k = 1; k < n_dev; k++) CUDA_TRY(cudaStreamWaitEvent(d0.stream, g.devs[k].done, 0));
+    CUDA_TRY(cudaEventRecord(r0, d0.stream));
+  }
+  if (n_dev > 1 && opt.reduce_mode == RT_GPU_REDUCE_NCCL) {
+    if (nccl_reduce_to_first(n_pixels * 3)) return 1;
+    CUDA_TRY(cudaSetDevice(d0.id));
+    int e = rt_launch_resolve(d0.d_accum, (int)im.width, (int)im.height, (int)ctx->samples, d0.d_image, (int)im.stride,
+                              im.components, d0.stream);
+    if (e) return fail("resolve kernel launch failed: %s", cudaGetErrorString((cudaError_t)e));
+  } else {
+    ReduceParts parts{};
+    parts.n = (int)n_dev;
+    for (size_t k = 0; k < n_dev; k++) parts.part[k] = g.devs[k].d_accum;
+    // one device: the same kernel with a single part (x + nothing) — one film code path for every N
+    int e = rt_launch_reduce_resolve(parts, n_dev > 1 ? d0.d_accum : nullptr, (int)im.width, (int)im.height, (int)ctx->samples,
+                                     d0.d_image, (int)im.stride, im.components, d0.stream);
+    if (e) return fail("reduce+resolve kernel launch failed: %s", cudaGetErrorString((cudaError_t)e));
+  }
   g.last_launches++;
-  CUDA_TRY(cudaMemcpyAsync(g.h_pinned, g.d_image, image_bytes, cudaMemcpyDeviceToHost, g.stream));
-  CUDA_TRY(cudaStreamSynchronize(g.stream));
-  memcpy(im.pixels.data, g.h_pinned, image_bytes);
+  if (r1) CUDA_TRY(cudaEventRecord(r1, d0.stream));
+  CUDA_TRY(cudaMemcpyAsync(d0.h_pinned, d0.d_image, image_bytes, cudaMemcpyDeviceToHost, d0.stream));
+  CUDA_TRY(cudaStreamSynchronize(d0.stream));
+  t0 = now_ms();
+  memcpy(im.pixels.data, d0.h_pinned, image_bytes);
+  g.last_d2h_ms = now_ms() - t0;
+  // peers keep their accumulators untouched until the reduce has read them: it has, the stream is drained
+  for (size_t k = 1; k < n_dev; k++) {
+    CUDA_TRY(cudaSetDevice(g.devs[k].id));
+    CUDA_TRY(cudaStreamSynchronize(g.devs[k].stream));
+  }
+  CUDA_TRY(cudaSetDevice(d0.id));
   float ms = 0;
-  cudaEventElapsedTime(&ms, g.ev0, g.ev1);
+  cudaEventElapsedTime(&ms, d0.ev0, d0.ev1);
   g.last_kernel_ms = ms;
+  g.last_reduce_ms = 0;
+  if (r0 && r1) {
+    cudaEventElapsedTime(&ms, r0, r1);
+    g.last_reduce_ms = ms;
+    cudaEventDestroy(r0);
+    cudaEventDestroy(r1);
+  }
+  cudaError_t late = cudaGetLastError();
+  if (late != cudaSuccess) return fail("render: %s", cudaGetErrorString(late));
   return 0;
 }
 
@@ -656,7 +683,12 @@ void render_thread_proc(Rendering_Context *ctx) {
   // raytracer.c:620: claim a chunk; whoever gets chunk 0 launches the whole frame
   i32 c = __atomic_fetch_add(const_cast<i32 *>(&ctx->_current_chunk), 1, __ATOMIC_SEQ_CST);
   if (c == 0) {
-    if (render_owner(ctx, n_chunks)) fprintf(stderr, "render_thread_proc: %s\n", rt_gpu_last_error());
+    clear_error();
+    g_status.store(0);
+    if (render_owner(ctx, n_chunks)) {
+      g_status.store(1);
+      fprintf(stderr, "render_thread_proc: %s\n", rt_gpu_last_error());
+    }
     __atomic_store_n(const_cast<i32 *>(&ctx->_current_chunk), (i32)n_chunks + 1, __ATOMIC_SEQ_CST);
   }
   // raytracer.c:622
@@ -674,6 +706,8 @@ void rendering_context_finish(Rendering_Context *ctx) {
 void lightmap_bake(Image const *, Scene const *, isize) {
   // Exported by the reference (raytracer.h:56) but never called;
   // out of scope for the GPU path, reported instead of silently ignored.
+  clear_error();
+  g_status.store(1);
   fail("lightmap_bake is not implemented on the GPU path");
   fprintf(stderr, "lightmap_bake: %s\n", rt_gpu_last_error());
 }
@@ -681,43 +715,51 @@ void lightmap_bake(Image const *, Scene const *, isize) {
 void denoise_image(Image const *src, Image const *dst, isize n_threads) {
   (void)n_threads;
   auto run = [&]() -> int {
-    if (ensure_init()) return 1;
     std::lock_guard<std::mutex> lock(g_mutex);
+    g.last_launches = 0;
+    if (ensure_init()) return 1;
+    if (!src->pixels.data || !dst->pixels.data) return fail("denoise: null pixel buffer");
     if (src->pixels.data == dst->pixels.data) return fail("denoise: src and dst must differ (reference denoiser.c:130)");
     if (src->width != dst->width || src->height != dst->height || src->components != dst->components)
       return fail("denoise: src and dst shapes differ (reference denoiser.c:131-132)");
-    CUDA_TRY(cudaSetDevice(g.device));
+    Device &d = g.devs[0];
+    CUDA_TRY(cudaSetDevice(d.id));
     const size_t src_bytes = (size_t)src->stride * (size_t)src->height * (size_t)src->components;
     const size_t dst_bytes = (size_t)dst->stride * (size_t)dst->height * (size_t)dst->components;
-    if (grow(reinterpret_cast<void **>(&g.d_image), &g.image_bytes, src_bytes)) return 1;
-    if (grow(reinterpret_cast<void **>(&g.d_image2), &g.image2_bytes, dst_bytes)) return 1;
-    if (grow_pinned(src_bytes > dst_bytes ? src_bytes : dst_bytes)) return 1;
-    g.last_launches = 0;
-    memcpy(g.h_pinned, src->pixels.data, src_bytes);
-    CUDA_TRY(cudaMemcpyAsync(g.d_image, g.h_pinned, src_bytes, cudaMemcpyHostToDevice, g.stream));
-    if (dst->stride != dst->width) CUDA_TRY(cudaMemsetAsync(g.d_image2, 0, dst_bytes, g.stream));
-    CUDA_TRY(cudaEventRecord(g.ev0, g.stream));
-    int e = rt_launch_denoise(g.d_image, g.d_image2, (int)src->width, (int)src->height, (int)src->stride, (int)dst->stride,
-                              src->components, g.stream);
+    CUDA_TRY(cudaStreamSynchronize(d.stream));
+    if (grow(reinterpret_cast<void **>(&d.d_image), &d.image_bytes, src_bytes)) return 1;
+    if (grow(reinterpret_cast<void **>(&d.d_image2), &d.image2_bytes, dst_bytes)) return 1;
+    if (grow_pinned(d, src_bytes > dst_bytes ? src_bytes : dst_bytes)) return 1;
+    memcpy(d.h_pinned, src->pixels.data, src_bytes);
+    CUDA_TRY(cudaMemcpyAsync(d.d_image, d.h_pinned, src_bytes, cudaMemcpyHostToDevice, d.stream));
+    if (dst->stride != dst->width) CUDA_TRY(cudaMemsetAsync(d.d_image2, 0, dst_bytes, d.stream));
+    CUDA_TRY(cudaEventRecord(d.ev0, d.stream));
+    int e = rt_launch_denoise(d.d_image, d.d_image2, (int)src->width, (int)src->height, (int)src->stride, (int)dst->stride,
+                              src->components, d.stream);
     if (e) return fail("denoise kernel launch failed: %s", cudaGetErrorString((cudaError_t)e));
     g.last_launches++;
-    CUDA_TRY(cudaEventRecord(g.ev1, g.stream));
-    CUDA_TRY(cudaMemcpyAsync(g.h_pinned, g.d_image2, dst_bytes, cudaMemcpyDeviceToHost, g.stream));
-    CUDA_TRY(cudaStreamSynchronize(g.stream));
+    CUDA_TRY(cudaEventRecord(d.ev1, d.stream));
+    CUDA_TRY(cudaMemcpyAsync(d.h_pinned, d.d_image2, dst_bytes, cudaMemcpyDeviceToHost, d.stream));
+    CUDA_TRY(cudaStreamSynchronize(d.stream));
     if (dst->stride == dst->width) {
-      memcpy(dst->pixels.data, g.h_pinned, dst_bytes);
+      memcpy(dst->pixels.data, d.h_pinned, dst_bytes);
     } else {
       for (isize y = 0; y < dst->height; y++)
         memcpy(dst->pixels.data + (size_t)y * (size_t)dst->stride * (size_t)dst->components,
-               g.h_pinned + (size_t)y * (size_t)dst->stride * (size_t)dst->components,
+               d.h_pinned + (size_t)y * (size_t)dst->stride * (size_t)dst->components,
                (size_t)dst->width * (size_t)dst->components);
     }
     float ms = 0;
-    cudaEventElapsedTime(&ms, g.ev0, g.ev1);
+    cudaEventElapsedTime(&ms, d.ev0, d.ev1);
     g.last_kernel_ms = ms;
     return 0;
   };
-  if (run()) fprintf(stderr, "denoise_image: %s\n", rt_gpu_last_error());
+  clear_error();
+  g_status.store(0);
+  if (run()) {
+    g_status.store(1);
+    fprintf(stderr, "denoise_image: %s\n", rt_gpu_last_error());
+  }
 }
 
 }  // extern "C"

@@ -57,9 +57,16 @@ struct SceneDev {
   float              focal_length;
 };
 
+#define RT_MAX_DEVICES 64    // CUDA device ordinals the library keeps per-device kernel attributes for
+#define RT_MAX_PARTS 16      // accumulators one reduce+resolve launch can combine
+
+struct ReduceParts { const float *part[RT_MAX_PARTS]; int n; };
+
 struct RenderParams {
   SceneDev  scene;
   int       width, height;
+  int       split_rank, split_world;     // pixel-space split over 32x32 chunks (rt_render.cu), world <= 1 = whole image
+  cudaEvent_t shading_ready;             // optional: textures/environment complete (the primary trace does not wait for it)
   int       sample_begin, sample_end, max_bounces;
   uint32_t  user_seed;
   int       accumulate;
@@ -67,6 +74,7 @@ struct RenderParams {
   float    *per_sample;
   int      *hit_ids;
   unsigned long long *counters;
+  unsigned long long *counters_ex;
 };
 
 __device__ __forceinline__ V3 mk3(float x, float y, float z) { V3 v; v.x = x; v.y = y; v.z = z; return v; }

@@ -7,11 +7,15 @@
 
 // wavefront render of samples [p.sample_begin, p.sample_end) into p.accum; `workspace` holds the path queues
 // (rt_render_workspace_bytes; a smaller one only means more, smaller chunks).  *n_launches += kernels launched.
-size_t rt_render_workspace_bytes(int width, int height, int n_samples, int max_bounces, int slice_samples);
+size_t rt_render_workspace_bytes(int width, int height, int n_samples, int max_bounces, int slice_samples, int split_world);
+unsigned rt_render_tiles(int width, int height, int split_rank, int split_world);
 int rt_launch_render(const RenderParams &p, int sm_count, void *workspace, size_t workspace_bytes,
                      cudaStream_t stream, int *n_launches);
 int rt_launch_resolve(const float *accum, int width, int height, int samples, unsigned char *pixels,
                       int stride, int components, cudaStream_t stream);
+// sum of parts.n accumulators (own + peer-mapped) in rank order, optional copy of the sum, optional resolve to u8
+int rt_launch_reduce_resolve(const ReduceParts &parts, float *sum_out, int width, int height, int samples,
+                             unsigned char *pixels, int stride, int components, cudaStream_t stream);
 int rt_launch_denoise(const unsigned char *src, unsigned char *dst, int width, int height,
                       int src_stride, int dst_stride, int components, cudaStream_t stream);
 int rt_render_blocks_per_sm(void);
@@ -21,5 +25,5 @@ int rt_launch_texel_repack(const unsigned char *src, int width, int height, int 
 // per-stage CUDA-event timing of rt_launch_render's kernels (off by default)
 // slot = stage * RT_STAGE_BOUNCES + min(bounce, RT_STAGE_BOUNCES - 1)
 enum { RT_STAGE_TRACE = 0, RT_STAGE_MISS, RT_STAGE_SHADE, RT_STAGE_ACCUMULATE, RT_N_STAGES, RT_STAGE_BOUNCES = 16 };
-void rt_stage_profile_enable(int on);
+void rt_stage_profile_enable(int on, int device);
 int  rt_stage_profile_read(double ms[RT_N_STAGES * RT_STAGE_BOUNCES], long long launches[RT_N_STAGES * RT_STAGE_BOUNCES]);

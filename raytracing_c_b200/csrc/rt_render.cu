@@ -55,6 +55,10 @@ struct StageParams {
   SceneDev   scene;
   PathQueues q;
   int        width, height, tiles_x, tiles_y;
+  // pixel-space split (multi-GPU at low spp): split_world > 1 = this render owns the reference's
+  // 32x32 chunks (raytracer.c:619-637) whose row-major id is congruent to split_rank; a chunk is 4 x 8 job tiles
+  int        split_rank, split_world, chunks_x;
+  unsigned   n_tiles;                 // job tiles (8x4 pixels) this render covers
   int        sample0, n_samples;      // this chunk: samples [sample0, sample0 + n_samples)
   int        bounce, max_bounces;
   uint32_t   user_seed;
@@ -65,6 +69,7 @@ struct StageParams {
   int        per_sample_stride, per_sample_offset;
   int       *hit_ids;                 // optional, written by the primary trace for sample `sample0`
   unsigned long long *counters;
+  unsigned long long *counters_ex;    // optional 8 more: [0] rays whose walk was the root-union test alone, [1] primary rays
 };
 
 // raytracer.c:582-594, one lane of hash12x8
@@ -78,12 +83,27 @@ __device__ __forceinline__ float hash12(float px, float py) {
   return fract1((a + b + d * 2.0f) * (c + d));
 }
 
+// top-left pixel of job tile `tile` (8x4 pixels): row-major over the image, or — pixel-space split — the
+// tile's place inside the k-th 32x32 chunk this rank owns (chunk id = k * split_world + split_rank)
+__device__ __forceinline__ void tile_origin(const StageParams &P, unsigned tile, int &x0, int &y0) {
+  if (P.split_world <= 1) {
+    x0 = (int)(tile % (unsigned)P.tiles_x) * 8;
+    y0 = (int)(tile / (unsigned)P.tiles_x) * 4;
+  } else {
+    const unsigned chunk = (tile >> 5) * (unsigned)P.split_world + (unsigned)P.split_rank, t = tile & 31u;
+    x0 = (int)(chunk % (unsigned)P.chunks_x) * 32 + (int)(t & 3u) * 8;
+    y0 = (int)(chunk / (unsigned)P.chunks_x) * 32 + (int)(t >> 2) * 4;      // beyond the last chunk row: y0 >= height
+  }
+}
+
 __device__ __forceinline__ void path_pixel(const StageParams &P, unsigned path, int &px, int &py, int &ls) {
   unsigned in_tile = path & 31u, rest = path >> 5;
   unsigned tile = rest / (unsigned)P.n_samples;
   ls = (int)(rest - tile * (unsigned)P.n_samples);
-  px = (int)(tile % (unsigned)P.tiles_x) * 8 + (int)(in_tile & 7u);
-  py = (int)(tile / (unsigned)P.tiles_x) * 4 + (int)(in_tile >> 3);
+  int x0, y0;
+  tile_origin(P, tile, x0, y0);
+  px = x0 + (int)(in_tile & 7u);
+  py = y0 + (int)(in_tile >> 3);
 }
 
 __device__ __forceinline__ void add_counter(unsigned long long *counters, int k, unsigned v) {
@@ -161,7 +181,7 @@ rt_trace_kernel(const __grid_constant__ StageParams P) {
   float4 *levels = level_store + threadIdx.x;
   unsigned *counts = P.q.counts + P.bounce * Q_STRIDE;
   const unsigned n_in = PRIMARY ? P.n_paths : counts[Q_RAYS];
-  unsigned c_rays = 0, c_nodes = 0, c_leaves = 0, c_accepts = 0;
+  unsigned c_rays = 0, c_nodes = 0, c_leaves = 0, c_accepts = 0, c_root_miss = 0;
 
   const float inv_w = 1.0f / (float)P.width, inv_h = 1.0f / (float)P.height;
   const float aspect = (float)P.width / (float)P.height;
@@ -273,7 +293,7 @@ rt_trace_kernel(const __grid_constant__ StageParams P) {
             walk_begin(w, sc, ox, oy, oz, dx, dy, dz);
             has_ray = true;
             c_rays++;
-            if (walk_misses_root<PRIMARY>(w, sc)) { w.done = true; c_nodes++; }      // the root visit, nothing entered
+            if (walk_misses_root<PRIMARY>(w, sc)) { w.done = true; c_nodes++; c_root_miss++; }      // the root visit, nothing entered
           }
         }
         range_next += take;
@@ -307,6 +327,10 @@ rt_trace_kernel(const __grid_constant__ StageParams P) {
     add_counter(P.counters, 1, c_nodes);
     add_counter(P.counters, 2, c_leaves);
     add_counter(P.counters, 3, c_accepts);
+  }
+  if (P.counters_ex) {
+    add_counter(P.counters_ex, 0, c_root_miss);
+    if (PRIMARY) add_counter(P.counters_ex, 1, c_rays);
   }
 }
 
@@ -440,11 +464,12 @@ rt_shade_kernel(const __grid_constant__ StageParams P) {
 // raytracer.c:696-700: color += cast_ray(...) in sample order, one thread per pixel.
 __global__ void __launch_bounds__(256)
 rt_accumulate_kernel(const __grid_constant__ StageParams P) {
-  const unsigned n = (unsigned)(P.tiles_x * P.tiles_y) * 32u;
+  const unsigned n = P.n_tiles * 32u;
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const unsigned tile = i >> 5, in_tile = i & 31u;
-    const int px = (int)(tile % (unsigned)P.tiles_x) * 8 + (int)(in_tile & 7u);
-    const int py = (int)(tile / (unsigned)P.tiles_x) * 4 + (int)(in_tile >> 3);
+    int x0, y0;
+    tile_origin(P, tile, x0, y0);
+    const int px = x0 + (int)(in_tile & 7u), py = y0 + (int)(in_tile >> 3);
     if (px >= P.width || py >= P.height) continue;
     const int pixel = py * P.width + px;
     V3 sum = P.accumulate ? mk3(P.accum[3 * pixel], P.accum[3 * pixel + 1], P.accum[3 * pixel + 2]) : mk3(0, 0, 0);
@@ -465,6 +490,15 @@ rt_accumulate_kernel(const __grid_constant__ StageParams P) {
 
 // ----------------------------------------------------------------------- film
 // raytracer.c:700-716 + common.h:90-92: /spp, clamp, sRGB OETF, *255.999, truncate.
+__device__ __forceinline__ unsigned char film_u8(float sum, float inv_samples) {
+  float v = sum * inv_samples;
+  if (v != v) v = 0;
+  v = clamp1(v, 0, 1);
+  v = (v <= 0.0031308f) ? (12.92f * v) : (1.055f * rt_powf(v, 1.0f / 2.4f) - 0.055f);
+  v = v * 255.999f;
+  return (unsigned char)v;
+}
+
 __global__ void rt_resolve_kernel(const float *__restrict__ accum, int width, int height, float inv_samples,
                                   unsigned char *__restrict__ pixels, int stride, int components) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -472,13 +506,49 @@ __global__ void rt_resolve_kernel(const float *__restrict__ accum, int width, in
   int x = i % width, y = i / width;
   unsigned char *dst = pixels + (size_t)components * (size_t)(x + y * stride);
   #pragma unroll
-  for (int c = 0; c < 3; c++) {
-    float v = accum[3 * i + c] * inv_samples;
-    if (v != v) v = 0;
-    v = clamp1(v, 0, 1);
-    v = (v <= 0.0031308f) ? (12.92f * v) : (1.055f * rt_powf(v, 1.0f / 2.4f) - 0.055f);
-    v = v * 255.999f;
-    dst[c] = (unsigned char)v;
+  for (int c = 0; c < 3; c++) dst[c] = film_u8(accum[3 * i + c], inv_samples);
+}
+
+// Multi-GPU film: the per-device accumulators are combined and resolved by ONE kernel on the device that owns
+// the image.  parts[k] are device pointers — this device's own buffer and its peers' buffers mapped over NVLink
+// (cudaDeviceEnablePeerAccess inside one process, cudaIpcOpenMemHandle across processes) — read with 16-byte loads
+// and summed in fixed rank order ((p0 + p1) + p2 ...), so the frame does not depend on which GPU finished first.
+// Replaces an ncclReduce into a staging buffer followed by rt_resolve_kernel: no round trip through HBM, no second launch.
+// One thread = four pixels = three float4 per part.
+__global__ void __launch_bounds__(256)
+rt_reduce_resolve_kernel(const ReduceParts parts, float *__restrict__ sum_out, int width, int height, float inv_samples,
+                         unsigned char *__restrict__ pixels, int stride, int components) {
+  const int n_pixels = width * height;
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  const int first = g * 4;
+  if (first >= n_pixels) return;
+  float v[12];
+  const int n_here = n_pixels - first < 4 ? n_pixels - first : 4;
+  if (n_here == 4) {
+    #pragma unroll
+    for (int q = 0; q < 3; q++) {
+      float4 s = reinterpret_cast<const float4 *>(parts.part[0])[3 * g + q];
+      for (int k = 1; k < parts.n; k++) {
+        const float4 t = reinterpret_cast<const float4 *>(parts.part[k])[3 * g + q];
+        s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+      }
+      v[4 * q] = s.x; v[4 * q + 1] = s.y; v[4 * q + 2] = s.z; v[4 * q + 3] = s.w;
+      if (sum_out) reinterpret_cast<float4 *>(sum_out)[3 * g + q] = s;
+    }
+  } else {
+    for (int j = 0; j < 3 * n_here; j++) {
+      float s = parts.part[0][3 * first + j];
+      for (int k = 1; k < parts.n; k++) s += parts.part[k][3 * first + j];
+      v[j] = s;
+      if (sum_out) sum_out[3 * first + j] = s;
+    }
+  }
+  if (!pixels) return;
+  for (int j = 0; j < n_here; j++) {
+    const int i = first + j, x = i % width, y = i / width;
+    unsigned char *dst = pixels + (size_t)components * (size_t)(x + y * stride);
+    #pragma unroll
+    for (int c = 0; c < 3; c++) dst[c] = film_u8(v[3 * j + c], inv_samples);
   }
 }
 
@@ -512,19 +582,30 @@ static size_t chunk_samples(size_t per_sample, int n_samples, int slice_samples)
   return s;
 }
 
-size_t rt_render_workspace_bytes(int width, int height, int n_samples, int max_bounces, int slice_samples) {
-  const size_t per_sample = (size_t)((width + 7) / 8) * (size_t)((height + 3) / 4) * 32;
+// job tiles (8x4 pixels) one render covers: the whole image, or the 32x32 chunks congruent to split_rank
+unsigned rt_render_tiles(int width, int height, int split_rank, int split_world) {
+  if (split_world <= 1) return (unsigned)((width + 7) / 8) * (unsigned)((height + 3) / 4);
+  const long chunks = (long)((width + 31) / 32) * (long)((height + 31) / 32);
+  const long owned = chunks > split_rank ? (chunks - split_rank + split_world - 1) / split_world : 0;
+  return (unsigned)owned * 32u;
+}
+
+size_t rt_render_workspace_bytes(int width, int height, int n_samples, int max_bounces, int slice_samples, int split_world) {
+  size_t per_sample = (size_t)rt_render_tiles(width, height, 0, split_world) * 32;
+  if (per_sample < 32) per_sample = 32;
   return counts_bytes(max_bounces > 0 ? max_bounces : 1) +
          chunk_samples(per_sample, n_samples, slice_samples) * per_sample * RT_PATH_BYTES;
 }
 
-static int g_trace_blocks_per_sm = 0;
-static size_t g_level_bytes = 0;
+// occupancy of the trace kernel and its dynamic-shared-memory opt-in, per device (cudaFuncSetAttribute is per device)
+static int g_trace_blocks_per_sm[RT_MAX_DEVICES];
+static size_t g_level_bytes[RT_MAX_DEVICES];
 
 // ---- optional per-stage timing (bench.py's roofline leg): CUDA events around every launch, on the
 // launching stream; read back and summed by rt_stage_profile_read
 struct StageEvent { cudaEvent_t a, b; int stage; };
 static bool g_profile = false;
+static int  g_profile_device = 0;        // launches on other devices of a multi-device frame are not timed
 static std::vector<StageEvent> g_stage_events;
 static std::vector<cudaEvent_t> g_event_pool;
 
@@ -537,14 +618,15 @@ static cudaEvent_t pooled_event() {
 
 struct StageTimer {
   cudaStream_t st; bool on; StageEvent ev;
-  StageTimer(int stage, cudaStream_t s) : st(s), on(g_profile) {
+  StageTimer(int stage, cudaStream_t s, int device) : st(s), on(g_profile && device == g_profile_device) {
     if (on) { ev.a = pooled_event(); ev.b = pooled_event(); ev.stage = stage; cudaEventRecord(ev.a, st); }
   }
   ~StageTimer() { if (on) { cudaEventRecord(ev.b, st); g_stage_events.push_back(ev); } }
 };
 
-void rt_stage_profile_enable(int on) {
+void rt_stage_profile_enable(int on, int device) {
   g_profile = on != 0;
+  g_profile_device = device;
   for (StageEvent &e : g_stage_events) { g_event_pool.push_back(e.a); g_event_pool.push_back(e.b); }
   g_stage_events.clear();
 }
@@ -581,29 +663,39 @@ int rt_launch_render(const RenderParams &p, int sm_count, void *workspace, size_
   }
   // level store: [depth][2][RT_BLOCK] float4 of dynamic shared memory (see rt_trace.cuh)
   const size_t level_bytes = (size_t)(p.scene.depth > 0 ? p.scene.depth : 1) * 2 * RT_BLOCK * sizeof(float4);
-  if (g_trace_blocks_per_sm == 0 || level_bytes != g_level_bytes) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= RT_MAX_DEVICES) return (int)cudaErrorInvalidDevice;
+  if (g_trace_blocks_per_sm[dev] == 0 || level_bytes != g_level_bytes[dev]) {
     int n = 0;
     cudaFuncSetAttribute(rt_trace_kernel<true>,  cudaFuncAttributeMaxDynamicSharedMemorySize, RT_MAX_DEPTH * 2 * RT_BLOCK * 16);
     cudaFuncSetAttribute(rt_trace_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RT_MAX_DEPTH * 2 * RT_BLOCK * 16);
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, rt_trace_kernel<false>, RT_BLOCK, level_bytes) != cudaSuccess || n < 1) n = 1;
-    g_trace_blocks_per_sm = n;
-    g_level_bytes = level_bytes;
+    g_trace_blocks_per_sm[dev] = n;
+    g_level_bytes[dev] = level_bytes;
   }
 
   StageParams P{};
   P.scene = p.scene;
   P.width = p.width; P.height = p.height;
   P.tiles_x = (p.width + 7) / 8; P.tiles_y = (p.height + 3) / 4;
+  P.split_rank = p.split_rank; P.split_world = p.split_world > 1 ? p.split_world : 1;
+  P.chunks_x = (p.width + 31) / 32;
+  P.n_tiles = rt_render_tiles(p.width, p.height, P.split_rank, P.split_world);
   P.max_bounces = p.max_bounces;
   P.user_seed = p.user_seed;
   P.accum = p.accum;
   P.per_sample = p.per_sample;
   P.per_sample_stride = n_total;
   P.counters = p.counters;
+  P.counters_ex = p.counters_ex;
 
   // chunking: as many samples of every pixel per chunk as the workspace holds paths
-  const size_t per_sample = (size_t)P.tiles_x * (size_t)P.tiles_y * 32;
+  const size_t per_sample = (size_t)P.n_tiles * 32;
   const size_t cb = counts_bytes(p.max_bounces);
+  if (P.split_world > 1 && !p.accumulate)      // the pixels of other ranks stay zero (the cross-rank sum adds them)
+    cudaMemsetAsync(p.accum, 0, (size_t)p.width * p.height * 3 * sizeof(float), stream);
+  if (per_sample == 0) return (int)cudaGetLastError();
   if (workspace_bytes < cb + per_sample * RT_PATH_BYTES) return (int)cudaErrorMemoryAllocation;
   size_t cap = (workspace_bytes - cb) / RT_PATH_BYTES;
   size_t fit = chunk_samples(per_sample, n_total, 0);
@@ -613,33 +705,36 @@ int rt_launch_render(const RenderParams &p, int sm_count, void *workspace, size_
   bind_queues(P.q, static_cast<char *>(workspace), cb, cap);
 
   rt_camera_relative_kernel<<<(unsigned)sm_count, 256, 0, stream>>>(p.scene);
-  const unsigned trace_grid = (unsigned)(sm_count * g_trace_blocks_per_sm);     // persistent: one wave
+  const unsigned trace_grid = (unsigned)(sm_count * g_trace_blocks_per_sm[dev]);     // persistent: one wave
   const unsigned flat_grid  = (unsigned)(sm_count * 8);
   int launches = 1;
   for (int s0 = p.sample_begin; s0 < p.sample_end; s0 += chunk) {
     const int S = (p.sample_end - s0 < chunk) ? p.sample_end - s0 : chunk;
     P.sample0 = s0; P.n_samples = S;
     P.n_paths = (unsigned)(per_sample * (size_t)S);
-    P.accumulate = (p.accumulate || s0 > p.sample_begin) ? 1 : 0;
+    P.accumulate = (p.accumulate || s0 > p.sample_begin || P.split_world > 1) ? 1 : 0;
     P.per_sample_offset = s0 - p.sample_begin;
     P.hit_ids = (s0 == p.sample_begin) ? p.hit_ids : nullptr;
     cudaMemsetAsync(P.q.counts, 0, cb, stream);
     P.bounce = 0;
-    { StageTimer t(RT_STAGE_TRACE * RT_STAGE_BOUNCES, stream); rt_trace_kernel<true><<<trace_grid, RT_BLOCK, level_bytes, stream>>>(P); }
+    { StageTimer t(RT_STAGE_TRACE * RT_STAGE_BOUNCES, stream, dev); rt_trace_kernel<true><<<trace_grid, RT_BLOCK, level_bytes, stream>>>(P); }
     launches++;
+    // textures and the environment may still be in flight on the upload's copy stream: the primary trace reads
+    // nodes and triangles only, everything after it waits here (rt_scene.cu)
+    if (s0 == p.sample_begin && p.shading_ready) cudaStreamWaitEvent(stream, p.shading_ready, 0);
     for (int b = 0; b < p.max_bounces; b++) {
       P.bounce = b;
       const int bslot = b < RT_STAGE_BOUNCES ? b : RT_STAGE_BOUNCES - 1;
       if (b > 0) {
-        StageTimer t(RT_STAGE_TRACE * RT_STAGE_BOUNCES + bslot, stream);
+        StageTimer t(RT_STAGE_TRACE * RT_STAGE_BOUNCES + bslot, stream, dev);
         rt_trace_kernel<false><<<trace_grid, RT_BLOCK, level_bytes, stream>>>(P);
         launches++;
       }
-      { StageTimer t(RT_STAGE_MISS * RT_STAGE_BOUNCES + bslot, stream);  rt_miss_kernel<<<flat_grid, 256, 0, stream>>>(P); }
-      { StageTimer t(RT_STAGE_SHADE * RT_STAGE_BOUNCES + bslot, stream); rt_shade_kernel<<<flat_grid, 256, 0, stream>>>(P); }
+      { StageTimer t(RT_STAGE_MISS * RT_STAGE_BOUNCES + bslot, stream, dev);  rt_miss_kernel<<<flat_grid, 256, 0, stream>>>(P); }
+      { StageTimer t(RT_STAGE_SHADE * RT_STAGE_BOUNCES + bslot, stream, dev); rt_shade_kernel<<<flat_grid, 256, 0, stream>>>(P); }
       launches += 2;
     }
-    { StageTimer t(RT_STAGE_ACCUMULATE * RT_STAGE_BOUNCES, stream); rt_accumulate_kernel<<<flat_grid, 256, 0, stream>>>(P); }
+    { StageTimer t(RT_STAGE_ACCUMULATE * RT_STAGE_BOUNCES, stream, dev); rt_accumulate_kernel<<<flat_grid, 256, 0, stream>>>(P); }
     launches++;
   }
   if (n_launches) *n_launches += launches;
@@ -654,4 +749,16 @@ int rt_launch_resolve(const float *accum, int width, int height, int samples, un
   return (int)cudaGetLastError();
 }
 
-int rt_render_blocks_per_sm(void) { return g_trace_blocks_per_sm; }
+int rt_launch_reduce_resolve(const ReduceParts &parts, float *sum_out, int width, int height, int samples,
+                             unsigned char *pixels, int stride, int components, cudaStream_t stream) {
+  const int groups = (width * height + 3) / 4;
+  const float inv_samples = 1.0f / (float)samples;
+  rt_reduce_resolve_kernel<<<(groups + 255) / 256, 256, 0, stream>>>(parts, sum_out, width, height, inv_samples, pixels, stride, components);
+  return (int)cudaGetLastError();
+}
+
+int rt_render_blocks_per_sm(void) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev >= 0 && dev < RT_MAX_DEVICES ? g_trace_blocks_per_sm[dev] : 0;
+}

@@ -38,6 +38,7 @@ class LoadedScene:
     background_proc: int
     path: str
     n_triangles: int
+    foreign_builder: bool = False      # scene buffers came from a test's builder (plain aligned_alloc), not scene_init
     _closed: bool = field(default=False)
 
     def close(self) -> None:
@@ -47,9 +48,25 @@ class LoadedScene:
         if _ffi._gpu is not None:
             gpu_lib().rt_gpu_scene_release(C.byref(self.scene))
         host = host_lib()
-        host.scene_destroy(C.byref(self.scene))
+        if self.foreign_builder:
+            libc = C.CDLL(None)
+            libc.free.argtypes = [C.c_void_p]
+            libc.free(self.scene.bvh.nodes.data)
+            libc.free(self.scene.triangles.x[0])
+        else:
+            host.scene_destroy(C.byref(self.scene))
         host.rt_model_free(C.byref(self.model))
         host.rt_image_free(C.byref(self.background))
+
+
+def use_pinned_host_buffers(on: bool = True) -> None:
+    """Texels, BVH nodes, the triangle block and images loaded from now on live in pinned memory
+    (rt_gpu_host_alloc), so rt_gpu_scene_upload DMA-reads them in place instead of staging them."""
+    if on:
+        gpu = gpu_lib()
+        host_lib().rt_host_set_buffer_allocator(fn_address(gpu.rt_gpu_host_alloc), fn_address(gpu.rt_gpu_host_free))
+    else:
+        host_lib().rt_host_set_buffer_allocator(None, None)
 
 
 def look_at(eye, target, up=(0.0, 1.0, 0.0), fov_degrees: float = 70.0) -> Camera:
@@ -88,7 +105,8 @@ def load_scene(path: str, shader_proc: Optional[int] = None, background_proc: Op
         scene.camera = camera
     scene.background.proc = background_proc
     loaded = LoadedScene(model=model, scene=scene, background=background, shader_proc=shader_proc,
-                         background_proc=background_proc, path=path, n_triangles=model.triangles.len)
+                         background_proc=background_proc, path=path, n_triangles=model.triangles.len,
+                         foreign_builder=builder is not None)
     loaded.scene.background.data = C.addressof(loaded.background)
     (builder or host.scene_init)(C.byref(loaded.scene), model.triangles)
     return loaded
@@ -113,9 +131,17 @@ def image_view(pixels: np.ndarray) -> Image:
 
 
 def set_options(user_seed: int = 0, sample_begin: int = 0, sample_end: int = 0, slice_samples: int = 64,
-                keep_hit_ids: bool = False) -> None:
-    opt = GPUOptions(user_seed, sample_begin, sample_end, slice_samples, int(keep_hit_ids))
+                keep_hit_ids: bool = False, sample_range_set: bool = False, split_mode: int = 0, reduce_mode: int = 0,
+                pixel_rank: int = 0, pixel_world: int = 0) -> None:
+    opt = GPUOptions(user_seed, sample_begin, sample_end, slice_samples, int(keep_hit_ids), int(sample_range_set),
+                     split_mode, reduce_mode, pixel_rank, pixel_world)
     gpu_lib().rt_gpu_set_options(C.byref(opt))
+
+
+def init_devices(n: int, devices=None) -> None:
+    """rt_gpu_init_devices: this process drives `n` GPUs (the host program's --gpus N)."""
+    ids = (C.c_int * n)(*devices) if devices is not None else None
+    gpu_check(gpu_lib().rt_gpu_init_devices(n, ids))
 
 
 def render(loaded: LoadedScene, width: int = DEFAULT_WIDTH, height: int = DEFAULT_HEIGHT,
@@ -140,9 +166,8 @@ def render(loaded: LoadedScene, width: int = DEFAULT_WIDTH, height: int = DEFAUL
         t.join()
     if not gpu.rendering_context_is_finished(C.byref(ctx)):
         raise RuntimeError("render did not finish")
-    err = gpu.rt_gpu_last_error()
-    if err and gpu.rt_gpu_last_launches() == 0:
-        raise RuntimeError("libraytracer_gpu: " + err.decode())
+    if gpu.rt_gpu_last_status() != 0:         # the entry points return void (raytracer.h:51-56)
+        raise RuntimeError("libraytracer_gpu: " + gpu.rt_gpu_last_error().decode())
     return pixels
 
 
@@ -153,7 +178,7 @@ def denoise(src: np.ndarray, n_threads: int = 1) -> np.ndarray:
     dst = np.zeros_like(src)
     a, b = image_view(src), image_view(dst)
     gpu.denoise_image(C.byref(a), C.byref(b), n_threads)
-    if gpu.rt_gpu_last_launches() == 0:
+    if gpu.rt_gpu_last_status() != 0:
         raise RuntimeError("libraytracer_gpu: " + gpu.rt_gpu_last_error().decode())
     return dst
 

@@ -12,7 +12,13 @@
  *                      exits instead, but its background.png is not in the tree)
  *   --eye x,y,z --target x,y,z [--fov degrees]   camera override
  *   --seed <u32>       per-(pixel,sample) seed
- *   --device <n>       CUDA device
+ *   --device <n>       CUDA device (first of --gpus)
+ *   --gpus <n>         devices this process drives (rt_gpu_init_devices): the frame is split over them, the
+ *                      accumulators are combined on the first one before the resolve and the denoise pass
+ *   --split auto|samples|chunks   how (RT_GPU_Options.split_mode)      --reduce p2p|nccl   with what
+ *   --dump-accum <file>    raw f32 W*H*3 sums of cast_ray (pre-division), little endian
+ *   --dump-hit-ids <file>  raw i32 W*H primary-hit slots of sample 0 (-1 = miss)
+ *   --pageable 1       keep host buffers in pageable memory (default: pinned, DMA-read in place)
  */
 #define _GNU_SOURCE
 #include <pthread.h>
@@ -31,7 +37,8 @@ typedef struct {
   bool verbose, denoise, has_eye, has_target;
   f32 eye[3], target[3], fov_degrees;
   u32 seed;
-  int device;
+  int device, gpus, split_mode, reduce_mode, pageable;
+  char const *dump_accum, *dump_hit_ids;
 } Config;
 
 static void print_usage(char const *argv0) {
@@ -59,6 +66,13 @@ static bool parse_args(int argc, char **argv, Config *c) {
       else if (!strcmp(arg, "--fov"))    c->fov_degrees = (f32)atof(val);
       else if (!strcmp(arg, "--seed"))   c->seed = (u32)strtoul(val, NULL, 10);
       else if (!strcmp(arg, "--device")) c->device = atoi(val);
+      else if (!strcmp(arg, "--gpus"))   c->gpus = atoi(val);
+      else if (!strcmp(arg, "--pageable")) c->pageable = atoi(val);
+      else if (!strcmp(arg, "--dump-accum"))   c->dump_accum = val;
+      else if (!strcmp(arg, "--dump-hit-ids")) c->dump_hit_ids = val;
+      else if (!strcmp(arg, "--split"))
+        c->split_mode = !strcmp(val, "samples") ? RT_GPU_SPLIT_SAMPLES : !strcmp(val, "chunks") ? RT_GPU_SPLIT_CHUNKS : RT_GPU_SPLIT_AUTO;
+      else if (!strcmp(arg, "--reduce")) c->reduce_mode = !strcmp(val, "nccl") ? RT_GPU_REDUCE_NCCL : RT_GPU_REDUCE_P2P;
       else { print_usage(argv[0]); return false; }
       i += 2;
       continue;
@@ -95,9 +109,13 @@ int main(int argc, char **argv) {
   f64 t_process = now_ms();
   /* driver.c:733-742 */
   Config config = { .width = 1024, .height = 1024, .samples = 16, .max_bounces = 8, .n_threads = 1,
-                    .output_path = "output.png", .env_path = "background.png", .fov_degrees = 70.0f };
+                    .output_path = "output.png", .env_path = "background.png", .fov_degrees = 70.0f, .gpus = 1 };
   if (!parse_args(argc, argv, &config)) return 1;
-  if (rt_gpu_init(config.device)) { fprintf(stderr, "%s\n", rt_gpu_last_error()); return 1; }
+  if (config.gpus < 1 || config.gpus > 16) { fprintf(stderr, "--gpus must be between 1 and 16\n"); return 1; }
+  int devices[16];
+  for (int i = 0; i < config.gpus; i++) devices[i] = config.device + i;
+  if (rt_gpu_init_devices(config.gpus, devices)) { fprintf(stderr, "%s\n", rt_gpu_last_error()); return 1; }
+  if (!config.pageable) rt_host_set_buffer_allocator(rt_gpu_host_alloc, rt_gpu_host_free);
 
   Image image = rt_image_alloc(config.width, config.height, 3);
 
@@ -135,6 +153,9 @@ int main(int argc, char **argv) {
   RT_GPU_Options options;
   rt_gpu_get_options(&options);
   options.user_seed = config.seed;
+  options.split_mode = config.split_mode;
+  options.reduce_mode = config.reduce_mode;
+  options.keep_hit_ids = config.dump_hit_ids != NULL;
   rt_gpu_set_options(&options);
 
   f64 t_render = now_ms();
@@ -163,16 +184,44 @@ int main(int argc, char **argv) {
   free(threads);
 
   f64 render_ms = now_ms() - t_render;
+  if (rt_gpu_last_status()) { fprintf(stderr, "render failed: %s\n", rt_gpu_last_error()); return 1; }
   printf("%ldms\n", (long)render_ms);
   if (config.verbose) {
     printf("%ld samples/second\n", (long)((f64)config.width * (f64)config.height * (f64)config.samples / (render_ms / 1e3)));
-    printf("GPU trace kernels: %.3fms in %d launches\n", rt_gpu_last_kernel_ms(), rt_gpu_last_launches());
+    f64 parts[4];
+    rt_gpu_last_frame_breakdown(parts);
+    printf("GPUs: %d (%s split), render kernels %.3fms in %d launches, reduce+resolve %.3fms, image D2H %.3fms\n", rt_gpu_device_count(),
+           parts[3] == RT_GPU_SPLIT_CHUNKS ? "chunk" : "sample", rt_gpu_last_kernel_ms(), rt_gpu_last_launches(), parts[1], parts[2]);
+  }
+  if (config.dump_accum || config.dump_hit_ids) {
+    size_t n = (size_t)config.width * (size_t)config.height;
+    if (config.dump_accum) {
+      f32 *accum = malloc(n * 3 * sizeof(f32));
+      FILE *f = fopen(config.dump_accum, "wb");
+      if (!accum || !f || rt_gpu_read_accum(accum, (isize)(n * 3)) || fwrite(accum, sizeof(f32), n * 3, f) != n * 3) {
+        fprintf(stderr, "--dump-accum failed: %s\n", rt_gpu_last_error());
+        return 1;
+      }
+      fclose(f);
+      free(accum);
+    }
+    if (config.dump_hit_ids) {
+      i32 *ids = malloc(n * sizeof(i32));
+      FILE *f = fopen(config.dump_hit_ids, "wb");
+      if (!ids || !f || rt_gpu_read_hit_ids(ids, (isize)n) || fwrite(ids, sizeof(i32), n, f) != n) {
+        fprintf(stderr, "--dump-hit-ids failed: %s\n", rt_gpu_last_error());
+        return 1;
+      }
+      fclose(f);
+      free(ids);
+    }
   }
 
   if (config.denoise) {
     f64 t0 = now_ms();
     Image denoised = rt_image_alloc(image.width, image.height, image.components);
     denoise_image(&image, &denoised, config.n_threads);
+    if (rt_gpu_last_status()) { fprintf(stderr, "denoise failed: %s\n", rt_gpu_last_error()); return 1; }
     rt_image_free(&image);
     image = denoised;
     printf("Denoising: %ldms\n", (long)(now_ms() - t0));

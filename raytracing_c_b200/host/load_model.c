@@ -564,7 +564,7 @@ bool rt_load_model_file(char const *path, Shader_Proc proc, RT_Model *model, Cam
 
 void rt_model_free(RT_Model *model) {
   free(model->triangles.data);
-  for (isize i = 0; i < model->n_images; i++) free(model->images[i].pixels.data);
+  for (isize i = 0; i < model->n_images; i++) rt_host_buffer_free(model->images[i].pixels.data);
   free(model->images);
   free(model->materials);
   memset(model, 0, sizeof *model);

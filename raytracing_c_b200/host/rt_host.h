@@ -49,6 +49,12 @@ bool rt_save_png(char const *path, Image const *image);
 bool rt_save_qoi(char const *path, Image const *image);
 bool rt_save_ppm(char const *path, Image const *image);
 
+/* Where texels, BVH nodes, the triangle block and images come from (default: aligned_alloc).  A GPU host installs
+ * rt_gpu_host_alloc / rt_gpu_host_free so these buffers are pinned and the scene upload DMA-reads them in place. */
+void  rt_host_set_buffer_allocator(void *(*alloc)(size_t), void (*release)(void *));
+void *rt_host_buffer_alloc(size_t bytes);
+void  rt_host_buffer_free(void *p);
+
 char const *rt_host_last_error(void);
 
 #ifdef __cplusplus

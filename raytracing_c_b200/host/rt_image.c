@@ -20,19 +20,50 @@ static _Thread_local char g_error[256];
 void rt_host_set_error(char const *msg) { snprintf(g_error, sizeof g_error, "%s", msg); }
 char const *rt_host_last_error(void) { return g_error; }
 
+/* Buffers the GPU library DMA-reads (texels, BVH nodes, triangle block) and writes (the output image) come from
+ * one hook, so a host can hand them out of pinned memory (rt_gpu_host_alloc: H2D then needs no staging copy).
+ * A 64-byte header in front of each buffer remembers which release function belongs to it, so the hook may be
+ * installed or changed at any time. */
+typedef struct { void (*release)(void *); u8 pad[64 - sizeof(void (*)(void *))]; } Buffer_Header;
+static void *(*g_buffer_alloc)(size_t) = NULL;
+static void (*g_buffer_release)(void *) = NULL;
+
+void rt_host_set_buffer_allocator(void *(*alloc)(size_t), void (*release)(void *)) {
+  g_buffer_alloc = alloc;
+  g_buffer_release = release;
+}
+
+void *rt_host_buffer_alloc(size_t bytes) {
+  size_t total = ((bytes + 63) & ~(size_t)63) + sizeof(Buffer_Header);
+  Buffer_Header *h = NULL;
+  void (*release)(void *) = free;
+  if (g_buffer_alloc && g_buffer_release) { h = g_buffer_alloc(total); release = g_buffer_release; }
+  if (!h) { h = aligned_alloc(64, total); release = free; }
+  if (!h) return NULL;
+  h->release = release;
+  return (u8 *)h + sizeof(Buffer_Header);
+}
+
+void rt_host_buffer_free(void *p) {
+  if (!p) return;
+  Buffer_Header *h = (Buffer_Header *)((u8 *)p - sizeof(Buffer_Header));
+  h->release(h);
+}
+
 Image rt_image_alloc(isize width, isize height, i32 components) {
   Image im;
   memset(&im, 0, sizeof im);
   im.width = width; im.height = height; im.stride = width;
   im.components = components; im.pixel_type = PT_u8;
   im.pixels.len = width * height * components;
-  im.pixels.data = aligned_alloc(64, ((size_t)im.pixels.len + 63) & ~(size_t)63);
+  im.pixels.data = rt_host_buffer_alloc((size_t)im.pixels.len);
+  if (!im.pixels.data) { rt_host_set_error("out of memory"); memset(&im, 0, sizeof im); return im; }
   memset(im.pixels.data, 0, (size_t)im.pixels.len);
   return im;
 }
 
 void rt_image_free(Image *image) {
-  free(image->pixels.data);
+  rt_host_buffer_free(image->pixels.data);
   memset(image, 0, sizeof *image);
 }
 

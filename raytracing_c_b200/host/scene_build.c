@@ -24,6 +24,7 @@
 #include <string.h>
 
 #include "scene.h"
+#include "rt_host.h"
 
 #ifndef RT_BUILD_THREADS
 #define RT_BUILD_THREADS 12   /* reference scene.c:425 */
@@ -224,12 +225,12 @@ void scene_init(Scene *scene, Triangle_Slice src) {
   scene->bvh.depth = depth;
   scene->bvh.last_row_offset = n_internal;
   scene->bvh.nodes.len = n_internal;
-  scene->bvh.nodes.data = aligned_alloc(64, (size_t)n_internal * sizeof(BVH_Node));
+  scene->bvh.nodes.data = rt_host_buffer_alloc((size_t)n_internal * sizeof(BVH_Node));
   memset(scene->bvh.nodes.data, 0, (size_t)n_internal * sizeof(BVH_Node));
 
   isize slots = bvh_n_leaf_nodes(depth) * RT_SIMD_WIDTH;
   size_t bytes = (TRIANGLES_ALLOCATION_SIZE(slots) + 63) & ~(size_t)63;
-  f32 *block = aligned_alloc(64, bytes);
+  f32 *block = rt_host_buffer_alloc(bytes);
   memset(block, 0, bytes);
   scene->triangles.len = (i32)slots;
   for (int v = 0; v < 3; v++) {
@@ -271,8 +272,8 @@ void scene_init(Scene *scene, Triangle_Slice src) {
 }
 
 void scene_destroy(Scene *scene) {
-  free(scene->bvh.nodes.data);
-  free(scene->triangles.x[0]);
+  rt_host_buffer_free(scene->bvh.nodes.data);
+  rt_host_buffer_free(scene->triangles.x[0]);
   memset(&scene->bvh, 0, sizeof scene->bvh);
   memset(&scene->triangles, 0, sizeof scene->triangles);
 }

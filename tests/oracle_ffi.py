@@ -29,7 +29,7 @@ class OracleOptions(C.Structure):
     _fields_ = [("seed_mode", C.c_int32), ("user_seed", C.c_uint32), ("approx_rsqrt", C.c_int32),
                 ("sample_begin", C.c_int32), ("sample_end", C.c_int32),
                 ("accum", C.c_void_p), ("per_sample", C.c_void_p), ("hit_ids", C.c_void_p),
-                ("counters", C.c_uint64 * 8)]
+                ("counters", C.c_uint64 * 8), ("pixel_mask", C.c_void_p)]
 
 
 def build_oracle() -> None:
@@ -75,8 +75,9 @@ def background_proc() -> int:
 
 def render(loaded, width, height, samples, max_bounces=8, n_threads=1, seed_mode=SEED_PER_SAMPLE, user_seed=0,
            sample_begin=0, sample_end=0, want_accum=True, want_per_sample=False, want_hit_ids=False,
-           approx_rsqrt=False):
-    """Runs the oracle's render_thread_proc restatement; returns a dict of numpy arrays."""
+           approx_rsqrt=False, pixel_mask=None):
+    """Runs the oracle's render_thread_proc restatement; returns a dict of numpy arrays.
+    `pixel_mask` (H, W) uint8: only pixels with a non-zero byte are rendered (the others stay 0)."""
     from raytracing_c_b200.driver import image_view
     pixels = np.zeros((height, width, 3), dtype=np.uint8)
     ctx = RenderingContext()
@@ -97,6 +98,10 @@ def render(loaded, width, height, samples, max_bounces=8, n_threads=1, seed_mode
     if want_hit_ids:
         out["hit_ids"] = np.full((height, width), -1, dtype=np.int32)
         opt.hit_ids = out["hit_ids"].ctypes.data
+    if pixel_mask is not None:
+        pixel_mask = np.ascontiguousarray(pixel_mask, dtype=np.uint8)
+        assert pixel_mask.shape == (height, width)
+        opt.pixel_mask = pixel_mask.ctypes.data
     lib().oracle_render(C.byref(ctx), C.byref(opt), n_threads)
     out["counters"] = {k: int(v) for k, v in zip(COUNTER_NAMES, opt.counters)}
     return out
