@@ -351,7 +351,8 @@ def run_gpu(args) -> None:
     pixels = torch.zeros(H * W * 3, dtype=torch.uint8, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     flag = torch.zeros(1, dtype=torch.int32, device=dev)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)      # a real stream (not the legacy default one): stream attributes apply
+    torch.cuda.set_stream(stream)
     sptr = C.c_void_p(stream.cuda_stream)
     launches = {"n": 0}
     mode_used = C.c_int32(SPLIT_SAMPLES)

@@ -315,6 +315,8 @@ void rt_gpu_set_options(RT_GPU_Options const *options) {
   std::lock_guard<std::mutex> lock(g_mutex);
   g.options = *options;
   if (g.options.slice_samples < 1) g.options.slice_samples = 64;
+  // the communicator costs seconds to create: when the NCCL film is asked for, do it here, not inside the first frame
+  if (g.ready && g.devs.size() > 1 && g.options.reduce_mode == RT_GPU_REDUCE_NCCL) nccl_prepare();
 }
 
 void rt_gpu_get_options(RT_GPU_Options *options) {
@@ -580,6 +582,19 @@ static int render_owner(Rendering_Context *ctx, isize n_chunks) {
     }
     const isize n_slices = (sh.s_end - sh.s_begin + slice - 1) / slice;
     if (n_slices > max_slices) max_slices = n_slices;
+  }
+  // Path-queue workspaces first, for every device, before anything is launched: with peer access enabled a
+  // cudaMalloc maps the new block into every peer and waits for whatever those peers are running.
+  for (size_t k = 0; k < n_dev; k++) {
+    Device &d = g.devs[k];
+    const Share &sh = shares[k];
+    const isize n = sh.s_end - sh.s_begin < slice ? sh.s_end - sh.s_begin : slice;
+    if (n <= 0) continue;
+    CUDA_TRY(cudaSetDevice(d.id));
+    const size_t want = rt_render_workspace_bytes((int)im.width, (int)im.height, (int)n, (int)ctx->max_bounces,
+                                                  opt.slice_samples, sh.split_world);
+    const size_t floor_bytes = rt_render_workspace_bytes((int)im.width, (int)im.height, 1, (int)ctx->max_bounces, 1, sh.split_world);
+    if (ensure_workspace(d, want, floor_bytes, d.stream)) return 1;
   }
   // slices round-robin over the devices, so the host's progress bar (driver.c:810-818) follows all of them
   for (size_t k = 0; k < n_dev; k++) {

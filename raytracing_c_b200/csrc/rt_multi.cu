@@ -88,7 +88,7 @@ int nccl_load() {
     if (r_ != ncclSuccess) return fail("%s failed: %s", #expr, nccl.GetErrorString(r_));                      \
   } while (0)
 
-int nccl_reduce_to_first(size_t n_floats) {
+int nccl_prepare() {
   if (nccl_load()) return 1;
   const int n = (int)g.devs.size();
   if ((int)nccl.comms.size() != n) {
@@ -97,7 +97,14 @@ int nccl_reduce_to_first(size_t n_floats) {
     std::vector<int> ids;
     for (Device &d : g.devs) ids.push_back(d.id);
     NCCL_TRY(nccl.CommInitAll(nccl.comms.data(), n, ids.data()));
+    cudaSetDevice(g.devs[0].id);
   }
+  return 0;
+}
+
+int nccl_reduce_to_first(size_t n_floats) {
+  if (nccl_prepare()) return 1;
+  const int n = (int)g.devs.size();
   NCCL_TRY(nccl.GroupStart());
   for (int k = 0; k < n; k++) {
     Device &d = g.devs[(size_t)k];

@@ -298,7 +298,12 @@ rt_trace_kernel(const __grid_constant__ StageParams P) {
         }
         range_next += take;
       }
-      if (__ballot_sync(RT_FULL, has_ray) == 0) break;
+      if (__ballot_sync(RT_FULL, has_ray) == 0) {
+        // nothing taken: the queue is drained — or (chunk split) the 32 ids just taken were a job tile that lies
+        // outside the image, and the warp's reserved range goes on
+        if (exhausted) break;
+        continue;
+      }
     }
 
     if (PRIMARY) {

@@ -418,7 +418,7 @@ void set_l2_window(Device &d, const DeviceScene &ds, cudaStream_t stream) {
   if (whole && !ds.blocks.empty()) want = ds.blocks[0].bytes;
   if (want > d.l2_window_max) want = d.l2_window_max;
   const size_t carve = want < d.l2_persist_max ? want : d.l2_persist_max;
-  if (!d.l2_window_set) { cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, d.l2_persist_max); d.l2_window_set = true; }
+  if (!d.l2_window_set) { cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve); d.l2_window_set = true; }
   d.l2_stream = stream; d.l2_base = ds.hot_base;
   cudaStreamAttrValue attr{};
   attr.accessPolicyWindow.base_ptr = ds.hot_base;

@@ -117,6 +117,7 @@ void set_l2_window(Device &d, const DeviceScene &ds, cudaStream_t stream);
 
 // ---- rt_multi.cu
 int enable_peers();                                           // device 0 <-> every other device
+int nccl_prepare();                                           // load libnccl, one communicator per device
 int nccl_reduce_to_first(size_t n_floats);                    // d_accum of every device summed into devs[0].d_accum
 void nccl_shutdown();
 void ipc_close_all();

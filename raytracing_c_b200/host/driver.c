@@ -115,6 +115,7 @@ int main(int argc, char **argv) {
   int devices[16];
   for (int i = 0; i < config.gpus; i++) devices[i] = config.device + i;
   if (rt_gpu_init_devices(config.gpus, devices)) { fprintf(stderr, "%s\n", rt_gpu_last_error()); return 1; }
+  f64 t_init_done = now_ms();
   if (!config.pageable) rt_host_set_buffer_allocator(rt_gpu_host_alloc, rt_gpu_host_free);
 
   Image image = rt_image_alloc(config.width, config.height, 3);
@@ -135,7 +136,9 @@ int main(int argc, char **argv) {
 
   rt_camera_default(&scene.camera);
   RT_Model model;
+  f64 t_load = now_ms();
   if (!rt_load_model_file(config.model, rt_gpu_pbr_shader_proc, &model, &scene.camera)) return 1;
+  f64 t_load_done = now_ms();
   if (config.has_eye && config.has_target) {
     Vec3 eye = {{ config.eye[0], config.eye[1], config.eye[2] }}, target = {{ config.target[0], config.target[1], config.target[2] }}, up = {{ 0, 1, 0 }};
     rt_camera_look_at(&scene.camera, eye, target, up, config.fov_degrees * 3.14159265f / 180.0f);
@@ -149,7 +152,11 @@ int main(int argc, char **argv) {
            (long)config.width, (long)config.height, (long)config.samples, (long)config.max_bounces, (long)config.n_threads);
     printf("BVH-Nodes: %ld\nBVH-Depth: %ld\nTriangles: %ld\n\n", (long)scene.bvh.nodes.len, (long)scene.bvh.depth, (long)model.triangles.len);
   }
+  f64 t_upload = now_ms();
   if (rt_gpu_scene_upload(&scene)) { fprintf(stderr, "%s\n", rt_gpu_last_error()); return 1; }
+  if (config.verbose)
+    printf("GPU init %ldms, model load + texture decode %ldms, scene upload issued in %ldms\n", (long)(t_init_done - t_process),
+           (long)(t_load_done - t_load), (long)(now_ms() - t_upload));
   RT_GPU_Options options;
   rt_gpu_get_options(&options);
   options.user_seed = config.seed;

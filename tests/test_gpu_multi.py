@@ -41,6 +41,21 @@ def render_full(loaded, w, h, spp, **opt):
     return dict(pixels=px, accum=driver.read_accum(w, h), hit_ids=driver.read_hit_ids(w, h), counters=driver.read_counters())
 
 
+def test_chunk_split_at_1080p_with_job_tiles_outside_the_image():
+    """1080 rows = 33 chunk rows + 24 pixel rows: the last chunk row holds job tiles that lie entirely outside the
+    image; a warp that draws such a tile must go on with the rest of its reserved range."""
+    loaded = load("helmet.glb")
+    try:
+        w, h, spp = 1920, 1080, 8
+        full = render_full(loaded, w, h, spp)
+        total = np.zeros_like(full["accum"])
+        for r in range(2):
+            total += render_full(loaded, w, h, spp, pixel_rank=r, pixel_world=2)["accum"]
+        assert np.array_equal(total, full["accum"])
+    finally:
+        loaded.close()
+
+
 @pytest.mark.parametrize("world", [2, 3, 8])
 def test_chunk_split_shards_sum_bit_identically(world):
     """The chunk split gives every pixel to exactly one shard, all its samples in order: the sum over shards
