@@ -96,10 +96,22 @@ __device__ __forceinline__ void tile_origin(const StageParams &P, unsigned tile,
   }
 }
 
+// RT_PATH_LAYOUT 0: path id = (tile * S + s) * 32 + pixel-in-tile — a warp is one 8x4 pixel tile at one sample index.
+// RT_PATH_LAYOUT 1: path id = (tile * 32 + pixel-in-tile) * S + s — a warp is 32 consecutive samples of ONE pixel:
+// its primary rays differ by less than a pixel, so they walk the same nodes and test the same leaves.
+#ifndef RT_PATH_LAYOUT
+#define RT_PATH_LAYOUT 1
+#endif
 __device__ __forceinline__ void path_pixel(const StageParams &P, unsigned path, int &px, int &py, int &ls) {
+#if RT_PATH_LAYOUT == 1
+  const unsigned pix = path / (unsigned)P.n_samples;
+  ls = (int)(path - pix * (unsigned)P.n_samples);
+  const unsigned in_tile = pix & 31u, tile = pix >> 5;
+#else
   unsigned in_tile = path & 31u, rest = path >> 5;
   unsigned tile = rest / (unsigned)P.n_samples;
   ls = (int)(rest - tile * (unsigned)P.n_samples);
+#endif
   int x0, y0;
   tile_origin(P, tile, x0, y0);
   px = x0 + (int)(in_tile & 7u);
@@ -478,9 +490,15 @@ rt_accumulate_kernel(const __grid_constant__ StageParams P) {
     if (px >= P.width || py >= P.height) continue;
     const int pixel = py * P.width + px;
     V3 sum = P.accumulate ? mk3(P.accum[3 * pixel], P.accum[3 * pixel + 1], P.accum[3 * pixel + 2]) : mk3(0, 0, 0);
+#if RT_PATH_LAYOUT == 1
+    const float4 *r = P.q.rad + (size_t)i * (size_t)P.n_samples;
+    const size_t r_step = 1;
+#else
     const float4 *r = P.q.rad + ((size_t)tile * (size_t)P.n_samples) * 32 + in_tile;
+    const size_t r_step = 32;
+#endif
     for (int s = 0; s < P.n_samples; s++) {
-      const float4 v = r[(size_t)s * 32];
+      const float4 v = r[(size_t)s * r_step];
       sum = add3(sum, mk3(v.x, v.y, v.z));
       if (P.per_sample) {
         float *dst = P.per_sample + ((size_t)pixel * (size_t)P.per_sample_stride + (size_t)(P.per_sample_offset + s)) * 3;
