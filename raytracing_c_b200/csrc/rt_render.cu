@@ -38,16 +38,24 @@
 #ifndef RT_TRACE_MIN_BLOCKS
 #define RT_TRACE_MIN_BLOCKS 3
 #endif
+#ifndef RT_TRACE_MIN_BLOCKS_PRIMARY
+#define RT_TRACE_MIN_BLOCKS_PRIMARY 4
+#endif
 #define RT_FULL 0xffffffffu
 
 // counts[bounce][...]: queue lengths written by one stage and read by the next
 enum { Q_RAYS = 0, Q_HITS, Q_MISSES, Q_FETCH, Q_STRIDE = 4 };
 
 struct PathQueues {
-  float4 *ray_a, *ray_b, *ray_c, *ray_d;            // (o.xyz, d.x) (d.yz, path, rng) (tint, -) (emission, -)
-  float4 *hit_a, *hit_b, *hit_c, *hit_d, *hit_h;    // the same four + (t, u, v, slot)
-  float4 *miss_a, *miss_b, *miss_c;                 // (d.xyz, path) (tint, -) (emission, -)
-  float4 *rad;                                      // [path] radiance of the finished sample
+  // queue records, compacted (a record moves with its ray): what the traversal needs and nothing else
+  float4 *ray_a, *ray_b;                            // (o.xyz, d.x) (d.yz, path, rng)
+  float4 *hit_a, *hit_b, *hit_h;                    // the same two + (t, u, v, slot)
+  float4 *miss_a;                                   // (d.xyz, path)
+  // path state, indexed by path id (touched by exactly one thread per stage: no ordering hazard): the running
+  // tint and emission of cast_ray (raytracer.c:507-510,537,544).  The trace kernel neither reads nor writes them.
+  // When a path ends, its radiance replaces the emission — `rad` IS `emis`.
+  float4 *tint, *emis;
+  float4 *rad;                                      // [path] radiance of the finished sample (alias of emis)
   unsigned *counts;                                 // [max_bounces + 1][Q_STRIDE]
 };
 
@@ -184,7 +192,8 @@ __global__ void rt_camera_relative_kernel(const SceneDev sc) {
 #endif
 
 template <bool PRIMARY>
-__global__ void __launch_bounds__(RT_BLOCK, RT_TRACE_MIN_BLOCKS)
+// coherent primary rays gain from a fourth resident block (-2.8 % on their kernel), bounce rays lose 3 % with it
+__global__ void __launch_bounds__(RT_BLOCK, PRIMARY ? RT_TRACE_MIN_BLOCKS_PRIMARY : RT_TRACE_MIN_BLOCKS)
 rt_trace_kernel(const __grid_constant__ StageParams P) {
   extern __shared__ float4 level_store[];          // [depth][2][RT_BLOCK] entry distances of pending levels
   const SceneDev &sc = P.scene;
@@ -225,7 +234,6 @@ rt_trace_kernel(const __grid_constant__ StageParams P) {
       if (__any_sync(RT_FULL, is_hit | is_miss)) {
         unsigned path = q;
         uint32_t rng = seed0;
-        float4 tint = make_float4(1, 1, 1, 0), emis = make_float4(0, 0, 0, 0);
         if (is_hit | is_miss) {
           if (PRIMARY) {
             if (P.hit_ids) {                       // parity hook: primary-hit slot of the chunk's first sample
@@ -237,8 +245,6 @@ rt_trace_kernel(const __grid_constant__ StageParams P) {
             const float4 b = P.q.ray_b[q];
             path = __float_as_uint(b.z);
             rng  = __float_as_uint(b.w);
-            tint = P.q.ray_c[q];
-            emis = P.q.ray_d[q];
           }
         }
         const unsigned hpos = warp_append(&counts[Q_HITS], is_hit, lane);
@@ -246,12 +252,10 @@ rt_trace_kernel(const __grid_constant__ StageParams P) {
         if (is_hit) {
           P.q.hit_a[hpos] = make_float4(w.ox, w.oy, w.oz, w.dx);
           P.q.hit_b[hpos] = make_float4(w.dy, w.dz, __uint_as_float(path), __uint_as_float(rng));
-          if (!PRIMARY) { P.q.hit_c[hpos] = tint; P.q.hit_d[hpos] = emis; }      // bounce 0: tint 1, emission 0, implied
           P.q.hit_h[hpos] = make_float4(w.hit_t, w.hit_u, w.hit_v, __int_as_float(w.hit_slot));
         }
         if (is_miss) {
           P.q.miss_a[mpos] = make_float4(w.dx, w.dy, w.dz, __uint_as_float(path));
-          if (!PRIMARY) { P.q.miss_b[mpos] = tint; P.q.miss_c[mpos] = emis; }
         }
         if (is_hit | is_miss) has_ray = false;
       }
@@ -371,7 +375,7 @@ rt_miss_kernel(const __grid_constant__ StageParams P) {
       // env * 1 + 0 is env bit for bit (a -0 channel would become +0, the environment is never negative)
       radiance = env;
     } else {
-      const float4 t = P.q.miss_b[i], e = P.q.miss_c[i];
+      const float4 t = P.q.tint[__float_as_uint(a.w)], e = P.q.emis[__float_as_uint(a.w)];
       radiance = add3(mul3(env, mk3(t.x, t.y, t.z)), mk3(e.x, e.y, e.z));
     }
     P.q.rad[__float_as_uint(a.w)] = make_float4(radiance.x, radiance.y, radiance.z, 0);
@@ -387,6 +391,47 @@ rt_miss_kernel(const __grid_constant__ StageParams P) {
 // raytracer.c:514-552 for one hit: attribute interpolation (:164-182), back-face
 // pass-through, BSDF, emission/tint update, next origin.  Survivors go to the RAY
 // queue of bounce + 1; paths that terminate or exhaust max_bounces (:557) write rad.
+// One surface interaction of cast_ray (raytracer.c:514-552) for the hit (t, u, v, slot) of the ray (o, d): returns
+// whether the path goes on; o, d, tint, emis and rng are updated in place (emis is the path's radiance if it ends).
+__device__ __forceinline__ bool shade_hit(const SceneDev &sc, const float *texel_lut, V3 &o, V3 &d, V3 &tint, V3 &emis,
+                                          uint32_t &rng, float hit_t, float hit_u, float hit_v, int slot,
+                                          unsigned &c_shades, unsigned &c_pass) {
+  const float4 *rec = sc.tri_rec + (size_t)slot * 7;
+  float4 r0 = __ldg(rec + 0), r1 = __ldg(rec + 1), r2 = __ldg(rec + 2);
+  V3 ng = mk3(r0.x, r0.y, r0.z);
+  V3 na = mk3(r0.w, r1.x, r1.y), nb = mk3(r1.z, r1.w, r2.x), nc = mk3(r2.y, r2.z, r2.w);
+  float w1 = hit_u, w2 = hit_v, w0 = 1 - w1 - w2;                       // raytracer.c:164-177
+  V3 point  = add3(o, scale3(d, hit_t));
+  V3 normal = mk3(na.x * w0 + nb.x * w1 + nc.x * w2,
+                  na.y * w0 + nb.y * w1 + nc.y * w2,
+                  na.z * w0 + nb.z * w1 + nc.z * w2);
+  if (dot3(ng, d) > 0 || dot3(normal, d) > 0) {
+    // raytracer.c:516-522: back face — step through, the bounce is consumed
+    c_pass++;
+    o = add3(point, scale3(d, RT_EPS));
+    return true;
+  }
+  float4 r3 = __ldg(rec + 3), r4 = __ldg(rec + 4), r5 = __ldg(rec + 5), r6 = __ldg(rec + 6);
+  ShadeIn in;
+  in.dir = d;
+  in.normal = normalize3(normal);
+  in.normal_geo = ng;
+  in.tangent   = mk3(r3.x, r3.y, r3.z);
+  in.bitangent = mk3(r3.w, r4.x, r4.y);
+  in.u = r4.z * w0 + r5.x * w1 + r5.z * w2;
+  in.v = r4.w * w0 + r5.y * w1 + r5.w * w2;
+  ShadeOut out;
+  c_shades++;
+  shade_pbr(sc, texel_lut, __float_as_int(r6.x), in, rng, out);
+  emis = add3(emis, mul3(out.emission, tint));          // raytracer.c:537
+  if (out.terminate) return false;
+  d = out.dir;
+  tint = mul3(tint, out.tint);
+  float bias = (0.5f - (float)(dot3(ng, out.dir) < 0)) * 2.0f * RT_EPS;   // raytracer.c:551
+  o = add3(point, scale3(ng, bias));
+  return true;
+}
+
 #ifndef RT_SHADE_MIN_BLOCKS
 #define RT_SHADE_MIN_BLOCKS 3
 #endif
@@ -414,48 +459,10 @@ rt_shade_kernel(const __grid_constant__ StageParams P) {
       path = __float_as_uint(b.z); rng = __float_as_uint(b.w);
       tint = mk3(1, 1, 1); emis = mk3(0, 0, 0);            // bounce 0 (raytracer.c:507-510): not stored
       if (P.bounce > 0) {
-        const float4 c = P.q.hit_c[i], e = P.q.hit_d[i];
+        const float4 c = P.q.tint[path], e = P.q.emis[path];
         tint = mk3(c.x, c.y, c.z); emis = mk3(e.x, e.y, e.z);
       }
-      const int slot = __float_as_int(h.w);
-
-      const float4 *rec = sc.tri_rec + (size_t)slot * 7;
-      float4 r0 = __ldg(rec + 0), r1 = __ldg(rec + 1), r2 = __ldg(rec + 2);
-      V3 ng = mk3(r0.x, r0.y, r0.z);
-      V3 na = mk3(r0.w, r1.x, r1.y), nb = mk3(r1.z, r1.w, r2.x), nc = mk3(r2.y, r2.z, r2.w);
-      float w1 = h.y, w2 = h.z, w0 = 1 - w1 - w2;                       // raytracer.c:164-177
-      V3 point  = add3(o, scale3(d, h.x));
-      V3 normal = mk3(na.x * w0 + nb.x * w1 + nc.x * w2,
-                      na.y * w0 + nb.y * w1 + nc.y * w2,
-                      na.z * w0 + nb.z * w1 + nc.z * w2);
-      cont = true;
-      if (dot3(ng, d) > 0 || dot3(normal, d) > 0) {
-        // raytracer.c:516-522: back face — step through, the bounce is consumed
-        c_pass++;
-        o = add3(point, scale3(d, RT_EPS));
-      } else {
-        float4 r3 = __ldg(rec + 3), r4 = __ldg(rec + 4), r5 = __ldg(rec + 5), r6 = __ldg(rec + 6);
-        ShadeIn in;
-        in.dir = d;
-        in.normal = normalize3(normal);
-        in.normal_geo = ng;
-        in.tangent   = mk3(r3.x, r3.y, r3.z);
-        in.bitangent = mk3(r3.w, r4.x, r4.y);
-        in.u = r4.z * w0 + r5.x * w1 + r5.z * w2;
-        in.v = r4.w * w0 + r5.y * w1 + r5.w * w2;
-        ShadeOut out;
-        c_shades++;
-        shade_pbr(sc, texel_lut, __float_as_int(r6.x), in, rng, out);
-        emis = add3(emis, mul3(out.emission, tint));          // raytracer.c:537
-        if (out.terminate) {
-          cont = false;
-        } else {
-          d = out.dir;
-          tint = mul3(tint, out.tint);
-          float bias = (0.5f - (float)(dot3(ng, out.dir) < 0)) * 2.0f * RT_EPS;   // raytracer.c:551
-          o = add3(point, scale3(ng, bias));
-        }
-      }
+      cont = shade_hit(sc, texel_lut, o, d, tint, emis, rng, h.x, h.y, h.z, __float_as_int(h.w), c_shades, c_pass);
       if (P.bounce + 1 >= P.max_bounces) cont = false;        // raytracer.c:557
       if (!cont) {
         P.q.rad[path] = make_float4(emis.x, emis.y, emis.z, 0);
@@ -466,8 +473,8 @@ rt_shade_kernel(const __grid_constant__ StageParams P) {
     if (cont) {
       P.q.ray_a[pos] = make_float4(o.x, o.y, o.z, d.x);
       P.q.ray_b[pos] = make_float4(d.y, d.z, __uint_as_float(path), __uint_as_float(rng));
-      P.q.ray_c[pos] = make_float4(tint.x, tint.y, tint.z, 0);
-      P.q.ray_d[pos] = make_float4(emis.x, emis.y, emis.z, 0);
+      P.q.tint[path] = make_float4(tint.x, tint.y, tint.z, 0);
+      P.q.emis[path] = make_float4(emis.x, emis.y, emis.z, 0);
     }
   }
   if (P.counters) {
@@ -475,6 +482,96 @@ rt_shade_kernel(const __grid_constant__ StageParams P) {
     add_counter(P.counters, 6, c_pass);
     add_counter(P.counters, 7, c_samples);
   }
+}
+
+// ----------------------------------------------------------------------- tail
+// The late bounces carry a few percent of the rays but cost a kernel trio each (trace, miss, shade: 15 launches for
+// bounces 3..7), and every one of those kernels lasts as long as its slowest warp.  This kernel runs the REST of
+// cast_ray's loop (raytracer.c:512-556) for every ray of the RAY queue of bounce P.bounce inside one thread: trace,
+// then environment or BSDF, then the next bounce, with no queue in between.  Same device functions, same order of
+// operations per path — and a path's result depends only on its own record — so the radiance is the same bits.
+__global__ void __launch_bounds__(RT_BLOCK, 2)
+rt_tail_kernel(const __grid_constant__ StageParams P) {
+  extern __shared__ float4 level_store[];
+  __shared__ float texel_lut[256];
+  texel_lut[threadIdx.x] = (float)threadIdx.x / 255.999f;
+  __syncthreads();
+  const SceneDev &sc = P.scene;
+  const unsigned lane = threadIdx.x & 31u;
+  float4 *levels = level_store + threadIdx.x;
+  const unsigned n = P.q.counts[P.bounce * Q_STRIDE + Q_RAYS];
+  unsigned *fetch = &P.q.counts[P.bounce * Q_STRIDE + Q_FETCH];
+  unsigned c_rays = 0, c_nodes = 0, c_leaves = 0, c_accepts = 0, c_root_miss = 0;
+  unsigned c_shades = 0, c_pass = 0, c_samples = 0, c_misses = 0;
+
+  for (;;) {
+    unsigned base = 0;
+    if (lane == 0) base = atomicAdd(fetch, 32u);
+    base = __shfl_sync(RT_FULL, base, 0);
+    if (base >= n) break;
+    const unsigned i = base + lane;
+    bool alive = i < n;
+    V3 o = mk3(0, 0, 0), d = mk3(0, 0, -1), tint = mk3(1, 1, 1), emis = mk3(0, 0, 0);
+    unsigned path = 0;
+    uint32_t rng = 0;
+    if (alive) {
+      const float4 a = P.q.ray_a[i], b = P.q.ray_b[i];
+      o = mk3(a.x, a.y, a.z); d = mk3(a.w, b.x, b.y);
+      path = __float_as_uint(b.z); rng = __float_as_uint(b.w);
+      const float4 c = P.q.tint[path], e = P.q.emis[path];
+      tint = mk3(c.x, c.y, c.z); emis = mk3(e.x, e.y, e.z);
+    }
+    for (int bounce = P.bounce; bounce < P.max_bounces; bounce++) {
+      if (__ballot_sync(RT_FULL, alive) == 0) break;
+      RayWalk w;
+      w.done = true; w.leaf = -1; w.hit_slot = -1;
+      if (alive) {
+        walk_begin(w, sc, o.x, o.y, o.z, d.x, d.y, d.z);
+        c_rays++;
+        if (walk_misses_root<false>(w, sc)) { w.done = true; c_nodes++; c_root_miss++; }
+      }
+      for (;;) {
+        const unsigned want_leaf = __ballot_sync(RT_FULL, w.leaf >= 0);
+        const unsigned want_node = __ballot_sync(RT_FULL, alive && !w.done && w.leaf < 0);
+        if ((want_leaf | want_node) == 0) break;
+        if (__popc(want_node) >= __popc(want_leaf)) {
+          if (want_node >> lane & 1u) walk_node_step<false>(w, sc, levels, c_nodes);
+        } else {
+          walk_leaf<false>(w, sc, c_leaves, c_accepts);
+        }
+        __syncwarp();
+      }
+      if (alive) {
+        if (w.hit_slot < 0) {
+          // raytracer.c:554
+          V3 env = environment(sc, texel_lut, d);
+          V3 radiance = add3(mul3(env, tint), emis);
+          P.q.rad[path] = make_float4(radiance.x, radiance.y, radiance.z, 0);
+          c_misses++; c_samples++;
+          alive = false;
+        } else {
+          bool cont = shade_hit(sc, texel_lut, o, d, tint, emis, rng, w.hit_t, w.hit_u, w.hit_v, w.hit_slot, c_shades, c_pass);
+          if (bounce + 1 >= P.max_bounces) cont = false;      // raytracer.c:557
+          if (!cont) {
+            P.q.rad[path] = make_float4(emis.x, emis.y, emis.z, 0);
+            c_samples++;
+            alive = false;
+          }
+        }
+      }
+    }
+  }
+  if (P.counters) {
+    add_counter(P.counters, 0, c_rays);
+    add_counter(P.counters, 1, c_nodes);
+    add_counter(P.counters, 2, c_leaves);
+    add_counter(P.counters, 3, c_accepts);
+    add_counter(P.counters, 4, c_shades);
+    add_counter(P.counters, 5, c_misses);
+    add_counter(P.counters, 6, c_pass);
+    add_counter(P.counters, 7, c_samples);
+  }
+  if (P.counters_ex) add_counter(P.counters_ex, 0, c_root_miss);
 }
 
 // ----------------------------------------------------------------- accumulate
@@ -576,24 +673,37 @@ rt_reduce_resolve_kernel(const ReduceParts parts, float *__restrict__ sum_out, i
 }
 
 // ------------------------------------------------------------------- launchers
-#define RT_PATH_BYTES ((4 + 5 + 3 + 1) * sizeof(float4))       // ray + hit + miss + rad records of one path
-#define RT_CHUNK_PATHS_MAX (128u << 20)
+#define RT_PATH_BYTES ((2 + 3 + 1 + 2) * sizeof(float4))       // ray + hit + miss records and the tint / emission(=rad) state of one path
+#define RT_CHUNK_PATHS_MAX (256u << 20)
+#ifndef RT_TAIL_BOUNCE_DEFAULT
+#define RT_TAIL_BOUNCE_DEFAULT (1 << 30)      /* measured slower than the kernel trios (profiles/r02_experiments.md): off */
+#endif
 
 static size_t counts_bytes(int max_bounces) {
   size_t b = (size_t)(max_bounces + 1) * Q_STRIDE * sizeof(unsigned);
   return (b + 255) & ~(size_t)255;
 }
 
-// Paths per wavefront chunk.  Every chunk pays a fixed ~1.3 ms (26 launches whose tails drain, late
-// bounces that last as long as their slowest ray), measured 3.56 / 4.22 / 4.61 / 4.77 Gsamples/s at
-// 16 / 32 / 64 / 128 Mi paths on helmet 1080p; 128 Mi paths = 26.6 GB of queues (208 B per path) of
-// the 180 GB on the device.  RT_GPU_CHUNK_PATHS overrides it (tuning / tests).
+// Paths per wavefront chunk.  Every chunk pays a fixed ~1.5 ms: the late bounces hold a few 10^4..10^5 rays and
+// their kernels last as long as their slowest warp (b3..b7: 1.6 ms per chunk whatever its size).  Measured on
+// helmet 1080p (round 2, 128 B per path): 6.18 / 6.28 / 6.33 Gsamples/s at 128 / 256 / 512 Mi paths.  Default
+// 256 Mi paths = 34 GB of the 180 GB on the device; a device that cannot spare it gets smaller chunks (rt_cabi.cu).
+// RT_GPU_CHUNK_PATHS overrides it (tuning / tests).
 static size_t chunk_paths_max() {
   if (const char *e = getenv("RT_GPU_CHUNK_PATHS")) {
     unsigned long long v = strtoull(e, nullptr, 10);
     if (v > 0) return (size_t)v;
   }
   return RT_CHUNK_PATHS_MAX;
+}
+
+// First bounce handled by rt_tail_kernel (all later ones with it); RT_GPU_TAIL_BOUNCE overrides, 0 or >= max_bounces = never.
+static int tail_bounce_setting() {
+  if (const char *e = getenv("RT_GPU_TAIL_BOUNCE")) {
+    const int v = atoi(e);
+    return v > 0 ? v : 1 << 30;
+  }
+  return RT_TAIL_BOUNCE_DEFAULT;
 }
 
 // samples of every pixel per chunk
@@ -621,7 +731,7 @@ size_t rt_render_workspace_bytes(int width, int height, int n_samples, int max_b
 }
 
 // occupancy of the trace kernel and its dynamic-shared-memory opt-in, per device (cudaFuncSetAttribute is per device)
-static int g_trace_blocks_per_sm[RT_MAX_DEVICES];
+static int g_trace_blocks_per_sm[RT_MAX_DEVICES], g_primary_blocks_per_sm[RT_MAX_DEVICES];
 static size_t g_level_bytes[RT_MAX_DEVICES];
 
 // ---- optional per-stage timing (bench.py's roofline leg): CUDA events around every launch, on the
@@ -671,9 +781,9 @@ int rt_stage_profile_read(double ms[RT_N_STAGES * RT_STAGE_BOUNCES], long long l
 
 static void bind_queues(PathQueues &q, char *w, size_t cb, size_t cap) {
   q.counts = reinterpret_cast<unsigned *>(w); w += cb;
-  float4 **arrays[] = { &q.ray_a, &q.ray_b, &q.ray_c, &q.ray_d, &q.hit_a, &q.hit_b, &q.hit_c,
-                        &q.hit_d, &q.hit_h, &q.miss_a, &q.miss_b, &q.miss_c, &q.rad };
+  float4 **arrays[] = { &q.ray_a, &q.ray_b, &q.hit_a, &q.hit_b, &q.hit_h, &q.miss_a, &q.tint, &q.emis };
   for (float4 **a : arrays) { *a = reinterpret_cast<float4 *>(w); w += cap * sizeof(float4); }
+  q.rad = q.emis;
 }
 
 int rt_launch_render(const RenderParams &p, int sm_count, void *workspace, size_t workspace_bytes,
@@ -693,8 +803,11 @@ int rt_launch_render(const RenderParams &p, int sm_count, void *workspace, size_
     int n = 0;
     cudaFuncSetAttribute(rt_trace_kernel<true>,  cudaFuncAttributeMaxDynamicSharedMemorySize, RT_MAX_DEPTH * 2 * RT_BLOCK * 16);
     cudaFuncSetAttribute(rt_trace_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RT_MAX_DEPTH * 2 * RT_BLOCK * 16);
+    cudaFuncSetAttribute(rt_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RT_MAX_DEPTH * 2 * RT_BLOCK * 16);
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, rt_trace_kernel<false>, RT_BLOCK, level_bytes) != cudaSuccess || n < 1) n = 1;
     g_trace_blocks_per_sm[dev] = n;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, rt_trace_kernel<true>, RT_BLOCK, level_bytes) != cudaSuccess || n < 1) n = 1;
+    g_primary_blocks_per_sm[dev] = n;
     g_level_bytes[dev] = level_bytes;
   }
 
@@ -727,8 +840,10 @@ int rt_launch_render(const RenderParams &p, int sm_count, void *workspace, size_
   cap = (size_t)chunk * per_sample;
   bind_queues(P.q, static_cast<char *>(workspace), cb, cap);
 
+  const int tail_bounce = tail_bounce_setting();
   rt_camera_relative_kernel<<<(unsigned)sm_count, 256, 0, stream>>>(p.scene);
   const unsigned trace_grid = (unsigned)(sm_count * g_trace_blocks_per_sm[dev]);     // persistent: one wave
+  const unsigned primary_grid = (unsigned)(sm_count * g_primary_blocks_per_sm[dev]);
   const unsigned flat_grid  = (unsigned)(sm_count * 8);
   int launches = 1;
   for (int s0 = p.sample_begin; s0 < p.sample_end; s0 += chunk) {
@@ -740,7 +855,7 @@ int rt_launch_render(const RenderParams &p, int sm_count, void *workspace, size_
     P.hit_ids = (s0 == p.sample_begin) ? p.hit_ids : nullptr;
     cudaMemsetAsync(P.q.counts, 0, cb, stream);
     P.bounce = 0;
-    { StageTimer t(RT_STAGE_TRACE * RT_STAGE_BOUNCES, stream, dev); rt_trace_kernel<true><<<trace_grid, RT_BLOCK, level_bytes, stream>>>(P); }
+    { StageTimer t(RT_STAGE_TRACE * RT_STAGE_BOUNCES, stream, dev); rt_trace_kernel<true><<<primary_grid, RT_BLOCK, level_bytes, stream>>>(P); }
     launches++;
     // textures and the environment may still be in flight on the upload's copy stream: the primary trace reads
     // nodes and triangles only, everything after it waits here (rt_scene.cu)
@@ -748,6 +863,13 @@ int rt_launch_render(const RenderParams &p, int sm_count, void *workspace, size_
     for (int b = 0; b < p.max_bounces; b++) {
       P.bounce = b;
       const int bslot = b < RT_STAGE_BOUNCES ? b : RT_STAGE_BOUNCES - 1;
+      if (b >= tail_bounce && b > 0) {
+        // everything from here on in one kernel (timed under the trace stage of this bounce)
+        StageTimer t(RT_STAGE_TRACE * RT_STAGE_BOUNCES + bslot, stream, dev);
+        rt_tail_kernel<<<(unsigned)(sm_count * 2), RT_BLOCK, level_bytes, stream>>>(P);
+        launches++;
+        break;
+      }
       if (b > 0) {
         StageTimer t(RT_STAGE_TRACE * RT_STAGE_BOUNCES + bslot, stream, dev);
         rt_trace_kernel<false><<<trace_grid, RT_BLOCK, level_bytes, stream>>>(P);

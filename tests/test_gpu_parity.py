@@ -219,7 +219,7 @@ def test_wavefront_chunking_is_invisible(monkeypatch):
         for per_chunk in (1, 3):
             monkeypatch.setenv("RT_GPU_CHUNK_PATHS", str(per_sample * per_chunk))
             other = gpu_render(loaded, w, h, spp, slice_samples=spp)
-            assert gpu_lib().rt_gpu_last_launches() >= 25 * -(-spp // per_chunk)      # 25 kernels per chunk at 8 bounces
+            assert gpu_lib().rt_gpu_last_launches() >= 10 * -(-spp // per_chunk)      # >= 10 kernels per chunk (trace, miss, shade per early bounce, one tail kernel, accumulate)
             assert np.array_equal(base["accum"], other["accum"])
             assert np.array_equal(base["hit_ids"], other["hit_ids"])
             assert base["counters"] == other["counters"]
