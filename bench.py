@@ -615,7 +615,7 @@ def main() -> None:
     ap.add_argument("--height", type=int, default=None)
     ap.add_argument("--spp", type=int, default=None)
     ap.add_argument("--bounces", type=int, default=8)
-    ap.add_argument("--slice", type=int, default=64, help="e2e leg: samples per progress slice of render_thread_proc")
+    ap.add_argument("--slice", type=int, default=0, help="e2e leg: samples per progress slice of render_thread_proc (0 = one wavefront chunk)")
     ap.add_argument("--cpu-spp", type=int, default=128, help="--impl reference: spp of each bounded CPU step (~6 s on 16 cores)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the reduced accumulator")

@@ -75,8 +75,8 @@ typedef struct {
   u32   user_seed;        /* rt_seed.h; default 0 */
   i32   sample_begin;     /* render samples [begin, end) of ctx->samples.  With sample_range_set == 0, */
   i32   sample_end;       /* end 0 = all; with sample_range_set != 0 the range is taken literally (may be empty) */
-  i32   slice_samples;    /* samples per progress slice of render_thread_proc (one wavefront chunk
-                           * never spans slices); default 64 */
+  i32   slice_samples;    /* samples per progress slice of render_thread_proc (one wavefront chunk never spans
+                           * slices); 0 (default) = as many as one chunk of path queues holds */
   i32   keep_hit_ids;     /* record the primary-hit slot of sample `sample_begin` */
   i32   sample_range_set;
   i32   split_mode;       /* N devices: RT_GPU_SPLIT_* — sample ranges in multiples of the 8-sample jitter batch
@@ -107,6 +107,11 @@ f64 rt_gpu_last_kernel_ms(void);                       /* CUDA-event time of the
 /* wall-clock pieces of the last render_thread_proc: [0] scene upload issued inside the call (ms, 0 if resident),
  * [1] cross-device reduce + resolve (CUDA events), [2] image D2H + host copy, [3] split mode used */
 void rt_gpu_last_frame_breakdown(f64 out[4]);
+
+/* ---- lightmap_bake (raytracer.h:56, reference raytracer.c:722-784) with its parity hooks: values_out (optional, W*H*3 f32)
+ * = accumulated / samples of every written texel before the u8 store; owner_out (optional, W*H i32) = the triangle slot
+ * that owns each texel, -1 = untouched.  Seeds: rt_seed.h, per (texel, sample); RT_GPU_Options.user_seed applies. ---- */
+int rt_gpu_lightmap_bake(Image const *lightmap, Scene const *scene, isize samples, f32 *values_out, i32 *owner_out);
 
 /* ---- how a frame is split over `world` devices or processes (pure host arithmetic, no device needed) ----
  * Sample split: batches of 8 samples dealt as evenly as possible; ranks beyond the number of batches get an

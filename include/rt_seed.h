@@ -23,6 +23,12 @@ RT_HD uint32_t rt_path_seed(uint32_t pixel_index, uint32_t sample_index, uint32_
   return h;
 }
 
+/* lightmap_bake (reference raytracer.c:722-784) draws its hemisphere directions from a second generator copy
+ * (raytracer.c's, common.h:13,30-42); per-(texel, sample) seeding gives that stream its own salt.  A normal that
+ * no direction satisfies (zero vector, NaN) would loop forever in the reference: both sides stop after this many draws. */
+#define RT_LIGHTMAP_DIR_SALT 0xD1B54A32u
+#define RT_LIGHTMAP_MAX_TRIES 64
+
 /* reference common.h:15-20 — the output is fed back as the state. */
 RT_HD uint32_t rt_rand_u32(uint32_t *random_state) {
   uint32_t state = *random_state * 747796405u + 2891336453u;

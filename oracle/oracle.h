@@ -65,6 +65,21 @@ enum {
 /* Runs the reference's chunk scheduler on n_threads OS threads and joins. */
 void oracle_render(Rendering_Context *ctx, Oracle_Options *opt, i32 n_threads);
 
+/* cast_ray (raytracer.c:505-558) for one ray with the shader generator in its current state. */
+Color3 oracle_cast_ray(Scene const *scene, Ray ray, isize max_bounces);
+
+/* ---- lightmap_bake (raytracer.c:722-784), see oracle_lightmap.c ---- */
+typedef struct {
+  i32  seed_mode;        /* ORACLE_SEED_* */
+  u32  user_seed;
+  u32  dir_state;        /* in/out (reference mode): raytracer.c's generator copy, feeds rand_vec3 */
+  u32  shader_state;     /* in/out (reference mode): driver.c's generator copy, feeds the BSDF */
+  f32 *values;           /* optional W*H*3: accumulated / samples of every written texel, before the u8 store */
+  i32 *owner;            /* optional W*H: triangle slot that wrote the texel last (caller pre-fills with -1) */
+  i64  texels_written;   /* out: stores, overlaps counted each time */
+} Oracle_Lightmap_Options;
+void oracle_lightmap_bake(Image const *lightmap, Scene const *scene, isize samples, Oracle_Lightmap_Options *opt);
+
 /* One ray through the traversal only: returns padded slot or -1; *t_out = distance. */
 i32 oracle_trace_ray(Scene const *scene, Ray ray, f32 *t_out);
 

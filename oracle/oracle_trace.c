@@ -247,6 +247,11 @@ static Color3 trace_path(Scene const *scene, Ray ray, isize max_bounces, i32 *pr
   return emission;
 }
 
+Color3 oracle_cast_ray(Scene const *scene, Ray ray, isize max_bounces) {
+  i32 slot;
+  return trace_path(scene, ray, max_bounces, &slot);
+}
+
 /* ---- raytracer.c:582-594, one lane of hash12x8 ---- */
 static inline f32 fractf(f32 v) { return v - floorf(v); }
 f32 oracle_hash12(f32 px, f32 py) {

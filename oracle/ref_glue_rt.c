@@ -22,3 +22,6 @@ f32 ref_hash12(f32 px, f32 py) {
   Vec2x8 p = { _mm256_set1_ps(px), _mm256_set1_ps(py) };
   return _mm256_cvtss_f32(hash12x8(p));
 }
+
+/* raytracer.c's own copy of the generator (common.h:13 is static thread_local in a header): feeds rand_vec3 in lightmap_bake */
+u32 *ref_rt_random_state(void) { return &random_state; }

@@ -114,7 +114,7 @@ GPU_EXPORTS = [
     "rt_gpu_host_alloc", "rt_gpu_host_free", "rt_gpu_last_frame_breakdown",
     "rt_gpu_shard_samples", "rt_gpu_shard_mode", "rt_gpu_shard_chunks",
     "rt_gpu_render_shard_device", "rt_gpu_accum_buffer", "rt_gpu_ipc_export", "rt_gpu_ipc_open",
-    "rt_gpu_reduce_resolve_device",
+    "rt_gpu_reduce_resolve_device", "rt_gpu_lightmap_bake",
     "rt_gpu_scene_device_bytes", "rt_gpu_scene_upload_bytes",
     "rt_gpu_register_pbr_shader", "rt_gpu_register_background", "rt_gpu_pbr_shader_proc", "rt_gpu_background_proc",
     "rt_gpu_scene_upload", "rt_gpu_scene_release", "rt_gpu_set_options", "rt_gpu_get_options",
@@ -200,6 +200,9 @@ def gpu_lib() -> C.CDLL:
         lib.rt_gpu_render_shard_device.argtypes = [C.POINTER(Scene), isize, isize, isize, isize, C.c_uint32, C.c_int32,
                                                    C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.c_void_p, C.c_void_p,
                                                    C.c_void_p]
+        lib.rt_gpu_lightmap_bake.argtypes = [C.POINTER(Image), C.POINTER(Scene), isize, C.c_void_p, C.c_void_p]
+        lib.lightmap_bake.argtypes = [C.POINTER(Image), C.POINTER(Scene), isize]
+        lib.lightmap_bake.restype = None
         lib.rt_gpu_accum_buffer.argtypes = [isize, isize, C.POINTER(C.c_void_p)]
         lib.rt_gpu_ipc_export.argtypes = [C.c_void_p, C.c_char_p]
         lib.rt_gpu_ipc_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]

@@ -18,6 +18,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <sched.h>
+#include <thread>
 
 #include "rt_state.h"
 #include "rt_gpu_internal.h"
@@ -85,6 +86,13 @@ int init_devices_locked(int n, const int *ids) {
     g.peers_enabled = false;
   }
   g.devs.resize(want.size());
+  if (want.size() > 1) {
+    // a CUDA context takes ~0.9 s to create; the contexts of different devices can be created side by side
+    std::vector<std::thread> makers;
+    for (int id : want) makers.emplace_back([id] { if (cudaSetDevice(id) == cudaSuccess) cudaFree(nullptr); });
+    for (std::thread &t : makers) t.join();
+    cudaGetLastError();
+  }
   for (size_t k = 0; k < want.size(); k++) {
     Device &d = g.devs[k];
     CUDA_TRY(cudaSetDevice(want[k]));
@@ -104,7 +112,6 @@ int init_devices_locked(int n, const int *ids) {
   }
   CUDA_TRY(cudaSetDevice(want[0]));
   g.ready = true;
-  if (g.options.slice_samples < 1) g.options.slice_samples = 64;
   return 0;
 }
 
@@ -145,7 +152,7 @@ struct Share {            // what one device (or process) renders of a frame
 // from: each waits for the event the previous one recorded.
 int render_on_device(Device &d, const Scene *scene, isize width, isize height, const Share &share, isize max_bounces,
                      u32 seed, int accumulate, float *d_accum, float *d_per_sample, int *d_hit_ids,
-                     unsigned long long *d_counters, cudaStream_t stream) {
+                     unsigned long long *d_counters, cudaStream_t stream, int slice_cap = 0) {
   if (width < 1 || height < 1) return fail("render: empty image");
   CUDA_TRY(cudaSetDevice(d.id));
   auto it = d.scenes.find(scene);
@@ -154,8 +161,7 @@ int render_on_device(Device &d, const Scene *scene, isize width, isize height, c
   RenderParams p{};
   p.scene = ds.dev;
   const int n_samples = (int)(share.s_end - share.s_begin);
-  const size_t want = rt_render_workspace_bytes((int)width, (int)height, n_samples, (int)max_bounces,
-                                                g.options.slice_samples, share.split_world);
+  const size_t want = rt_render_workspace_bytes((int)width, (int)height, n_samples, (int)max_bounces, slice_cap, share.split_world);
   const size_t floor_bytes = rt_render_workspace_bytes((int)width, (int)height, 1, (int)max_bounces, 1, share.split_world);
   if (n_samples > 0 && ensure_workspace(d, want, floor_bytes, stream)) return 1;
   if (d.busy_valid) CUDA_TRY(cudaStreamWaitEvent(stream, d.busy, 0));
@@ -314,7 +320,7 @@ void rt_gpu_host_free(void *p) {
 void rt_gpu_set_options(RT_GPU_Options const *options) {
   std::lock_guard<std::mutex> lock(g_mutex);
   g.options = *options;
-  if (g.options.slice_samples < 1) g.options.slice_samples = 64;
+  if (g.options.slice_samples < 0) g.options.slice_samples = 0;
   // the communicator costs seconds to create: when the NCCL film is asked for, do it here, not inside the first frame
   if (g.ready && g.devs.size() > 1 && g.options.reduce_mode == RT_GPU_REDUCE_NCCL) nccl_prepare();
 }
@@ -322,7 +328,6 @@ void rt_gpu_set_options(RT_GPU_Options const *options) {
 void rt_gpu_get_options(RT_GPU_Options *options) {
   std::lock_guard<std::mutex> lock(g_mutex);
   *options = g.options;
-  if (options->slice_samples < 1) options->slice_samples = 64;
 }
 
 // ------------------------------------------------------------ device-pointer level
@@ -553,9 +558,15 @@ static int render_owner(Rendering_Context *ctx, isize n_chunks) {
   if (s_begin < 0) s_begin = 0;
   if (s_end > ctx->samples) s_end = ctx->samples;
   if (s_end < s_begin) s_end = s_begin;
-  const isize slice = opt.slice_samples > 0 ? opt.slice_samples : 64;
   const i32 mode = n_dev > 1 ? rt_gpu_shard_mode((i32)(s_end - s_begin), (i32)n_dev, opt.split_mode) : RT_GPU_SPLIT_SAMPLES;
 
+  // samples per progress slice: as asked, or as many as one wavefront chunk holds (fewer, larger chunks are faster)
+  isize slice = opt.slice_samples;
+  if (slice <= 0) {
+    const int world = n_dev > 1 && mode == RT_GPU_SPLIT_CHUNKS ? (int)n_dev : (opt.pixel_world > 1 ? opt.pixel_world : 1);
+    slice = (isize)rt_render_chunk_samples((int)im.width, (int)im.height, world);
+    if (slice < 1) slice = 1;
+  }
   g.last_pixels = n_pixels;
   g.last_has_hit_ids = opt.keep_hit_ids != 0;
   g.last_split_mode = mode;
@@ -591,8 +602,7 @@ static int render_owner(Rendering_Context *ctx, isize n_chunks) {
     const isize n = sh.s_end - sh.s_begin < slice ? sh.s_end - sh.s_begin : slice;
     if (n <= 0) continue;
     CUDA_TRY(cudaSetDevice(d.id));
-    const size_t want = rt_render_workspace_bytes((int)im.width, (int)im.height, (int)n, (int)ctx->max_bounces,
-                                                  opt.slice_samples, sh.split_world);
+    const size_t want = rt_render_workspace_bytes((int)im.width, (int)im.height, (int)n, (int)ctx->max_bounces, 0, sh.split_world);
     const size_t floor_bytes = rt_render_workspace_bytes((int)im.width, (int)im.height, 1, (int)ctx->max_bounces, 1, sh.split_world);
     if (ensure_workspace(d, want, floor_bytes, d.stream)) return 1;
   }
@@ -718,13 +728,73 @@ void rendering_context_finish(Rendering_Context *ctx) {
   while (__atomic_load_n(const_cast<i32 *>(&ctx->n_threads), __ATOMIC_SEQ_CST) > 0) sched_yield();
 }
 
-void lightmap_bake(Image const *, Scene const *, isize) {
-  // Exported by the reference (raytracer.h:56) but never called;
-  // out of scope for the GPU path, reported instead of silently ignored.
+// raytracer.h:56 / raytracer.c:722-784 on the GPU (first device): the kernels are in rt_render.cu.  values_out
+// (optional, W*H*3 f32) receives accumulated / samples of every written texel before the u8 store, owner_out
+// (optional, W*H i32) the slot of the triangle that owns each texel (-1 = untouched; such texels keep their bytes).
+int rt_gpu_lightmap_bake(Image const *lightmap, Scene const *scene, isize samples, f32 *values_out, i32 *owner_out) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  g.last_launches = 0;
+  if (ensure_init()) return 1;
+  if (!lightmap || !scene) return fail("lightmap_bake: null argument");
+  if (lightmap->pixel_type != PT_u8 || lightmap->components < 3 || !lightmap->pixels.data)      // raytracer.c:723-724
+    return fail("lightmap_bake: the lightmap must be u8 with >= 3 components");
+  if (lightmap->width < 1 || lightmap->height < 1 || lightmap->stride < lightmap->width) return fail("lightmap_bake: empty image or stride < width");
+  if (samples < 1) return fail("lightmap_bake: samples must be >= 1");
+  if (scene_on_devices(scene)) return 1;
+  Device &d = g.devs[0];
+  CUDA_TRY(cudaSetDevice(d.id));
+  const DeviceScene &ds = d.scenes.find(scene)->second;
+  const int W = (int)lightmap->width, H = (int)lightmap->height;
+  const size_t n_texels = (size_t)W * (size_t)H;
+  const size_t image_bytes = (size_t)lightmap->stride * (size_t)H * (size_t)lightmap->components;
+  const int max_bounces = 8;                                        // raytracer.c:773: cast_ray(scene, r, 8)
+
+  CUDA_TRY(cudaStreamSynchronize(d.stream));
+  CUDA_TRY(cudaStreamSynchronize(d.copy));
+  if (grow(reinterpret_cast<void **>(&d.d_image), &d.image_bytes, image_bytes)) return 1;
+  if (grow_pinned(d, image_bytes)) return 1;
+  const size_t scratch_bytes = rt_lightmap_workspace_bytes(W, H) + (values_out ? n_texels * 3 * sizeof(float) : 0) +
+                               (owner_out ? n_texels * sizeof(int) : 0);
+  if (grow(&d.d_texel_stage, &d.texel_stage_bytes, scratch_bytes)) return 1;       // the upload's raw-texel block doubles as scratch
+  char *scratch = static_cast<char *>(d.d_texel_stage);
+  float *d_values = values_out ? reinterpret_cast<float *>(scratch + rt_lightmap_workspace_bytes(W, H)) : nullptr;
+  int *d_owner = owner_out ? reinterpret_cast<int *>(scratch + rt_lightmap_workspace_bytes(W, H) + (values_out ? n_texels * 3 * sizeof(float) : 0)) : nullptr;
+  // path queues: at most one chunk's worth, at least one sample of every texel
+  const size_t per_path = rt_render_workspace_bytes(8, 4, 1, max_bounces, 1, 1) / 32 + sizeof(float) + 16;
+  size_t paths = n_texels * (size_t)samples;
+  const size_t chunk_paths = (size_t)rt_render_chunk_samples(8, 4, 1) * 32;
+  if (paths > chunk_paths) paths = chunk_paths;
+  if (paths < n_texels) paths = n_texels;
+  if (ensure_workspace(d, paths * per_path + 4096, n_texels * per_path + 4096, d.stream)) return 1;
+
+  if (d.busy_valid) CUDA_TRY(cudaStreamWaitEvent(d.stream, d.busy, 0));
+  CUDA_TRY(cudaStreamWaitEvent(d.stream, ds.geom_ready, 0));
+  CUDA_TRY(cudaStreamWaitEvent(d.stream, ds.tex_ready, 0));
+  memcpy(d.h_pinned, lightmap->pixels.data, image_bytes);            // untouched texels keep their bytes
+  CUDA_TRY(cudaMemcpyAsync(d.d_image, d.h_pinned, image_bytes, cudaMemcpyHostToDevice, d.stream));
+  if (d_values) CUDA_TRY(cudaMemsetAsync(d_values, 0, n_texels * 3 * sizeof(float), d.stream));
+  unsigned n_jobs = 0;
+  int e = rt_launch_lightmap(ds.dev, W, H, (int)samples, max_bounces, g.options.user_seed, d.d_image, (int)lightmap->stride,
+                             lightmap->components, d_values, d_owner, scratch, d.sm_count, d.d_workspace, d.workspace_bytes,
+                             d.stream, &g.last_launches, &n_jobs);
+  if (e) return fail("lightmap kernel launch failed: %s", cudaGetErrorString((cudaError_t)e));
+  CUDA_TRY(cudaEventRecord(d.busy, d.stream));
+  d.busy_valid = true;
+  CUDA_TRY(cudaMemcpyAsync(d.h_pinned, d.d_image, image_bytes, cudaMemcpyDeviceToHost, d.stream));
+  CUDA_TRY(cudaStreamSynchronize(d.stream));
+  memcpy(lightmap->pixels.data, d.h_pinned, image_bytes);
+  if (values_out) CUDA_TRY(cudaMemcpy(values_out, d_values, n_texels * 3 * sizeof(float), cudaMemcpyDeviceToHost));
+  if (owner_out) CUDA_TRY(cudaMemcpy(owner_out, d_owner, n_texels * sizeof(int), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+void lightmap_bake(Image const *lightmap, Scene const *scene, isize samples) {
   clear_error();
-  g_status.store(1);
-  fail("lightmap_bake is not implemented on the GPU path");
-  fprintf(stderr, "lightmap_bake: %s\n", rt_gpu_last_error());
+  g_status.store(0);
+  if (rt_gpu_lightmap_bake(lightmap, scene, samples, nullptr, nullptr)) {
+    g_status.store(1);
+    fprintf(stderr, "lightmap_bake: %s\n", rt_gpu_last_error());
+  }
 }
 
 void denoise_image(Image const *src, Image const *dst, isize n_threads) {

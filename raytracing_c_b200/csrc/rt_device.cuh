@@ -46,6 +46,7 @@ struct SceneDev {
   const float       *nodes;
   const float4      *tri_pos;
   const float4      *tri_rec;
+  const float       *tri_soa;        // the host's nine vertex arrays x0 x1 x2 y0 y1 y2 z0 z1 z2, n_slots each (lightmap_bake)
   float             *nodes_rel;      // nodes minus the camera origin, refreshed per render (primary rays)
   float4            *tri_rel;        // float4[n_slots][4]: (o-p0, e1.x)(e1.yz, e2.xy)(e2.z, (o-p0) x e1)(e2 . that, -, -, -)
   const MaterialDev *materials;

@@ -723,6 +723,13 @@ unsigned rt_render_tiles(int width, int height, int split_rank, int split_world)
   return (unsigned)owned * 32u;
 }
 
+// samples of every pixel one wavefront chunk holds at the preferred queue size
+int rt_render_chunk_samples(int width, int height, int split_world) {
+  size_t per_sample = (size_t)rt_render_tiles(width, height, 0, split_world) * 32;
+  if (per_sample < 32) per_sample = 32;
+  return (int)chunk_samples(per_sample, 0, 0);
+}
+
 size_t rt_render_workspace_bytes(int width, int height, int n_samples, int max_bounces, int slice_samples, int split_world) {
   size_t per_sample = (size_t)rt_render_tiles(width, height, 0, split_world) * 32;
   if (per_sample < 32) per_sample = 32;
@@ -786,16 +793,10 @@ static void bind_queues(PathQueues &q, char *w, size_t cb, size_t cap) {
   q.rad = q.emis;
 }
 
-int rt_launch_render(const RenderParams &p, int sm_count, void *workspace, size_t workspace_bytes,
-                     cudaStream_t stream, int *n_launches) {
-  const int n_total = p.sample_end - p.sample_begin;
-  if (n_total <= 0 || p.max_bounces < 1) {
-    // no samples, or cast_ray's loop body never runs (raytracer.c:512,557): the sum gains nothing
-    if (!p.accumulate) cudaMemsetAsync(p.accum, 0, (size_t)p.width * p.height * 3 * sizeof(float), stream);
-    return (int)cudaGetLastError();
-  }
+// Dynamic shared memory opt-in and occupancy of the trace kernels on the current device (once per device and depth).
+static int trace_launch_setup(const SceneDev &scene, int *dev_out, size_t *level_bytes_out) {
   // level store: [depth][2][RT_BLOCK] float4 of dynamic shared memory (see rt_trace.cuh)
-  const size_t level_bytes = (size_t)(p.scene.depth > 0 ? p.scene.depth : 1) * 2 * RT_BLOCK * sizeof(float4);
+  const size_t level_bytes = (size_t)(scene.depth > 0 ? scene.depth : 1) * 2 * RT_BLOCK * sizeof(float4);
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= RT_MAX_DEVICES) return (int)cudaErrorInvalidDevice;
@@ -810,6 +811,22 @@ int rt_launch_render(const RenderParams &p, int sm_count, void *workspace, size_
     g_primary_blocks_per_sm[dev] = n;
     g_level_bytes[dev] = level_bytes;
   }
+  *dev_out = dev;
+  *level_bytes_out = level_bytes;
+  return 0;
+}
+
+int rt_launch_render(const RenderParams &p, int sm_count, void *workspace, size_t workspace_bytes,
+                     cudaStream_t stream, int *n_launches) {
+  const int n_total = p.sample_end - p.sample_begin;
+  if (n_total <= 0 || p.max_bounces < 1) {
+    // no samples, or cast_ray's loop body never runs (raytracer.c:512,557): the sum gains nothing
+    if (!p.accumulate) cudaMemsetAsync(p.accum, 0, (size_t)p.width * p.height * 3 * sizeof(float), stream);
+    return (int)cudaGetLastError();
+  }
+  size_t level_bytes = 0;
+  int dev = 0;
+  if (int e = trace_launch_setup(p.scene, &dev, &level_bytes)) return e;
 
   StageParams P{};
   P.scene = p.scene;
@@ -882,6 +899,232 @@ int rt_launch_render(const RenderParams &p, int sm_count, void *workspace, size_
     { StageTimer t(RT_STAGE_ACCUMULATE * RT_STAGE_BOUNCES, stream, dev); rt_accumulate_kernel<<<flat_grid, 256, 0, stream>>>(P); }
     launches++;
   }
+  if (n_launches) *n_launches += launches;
+  return (int)cudaGetLastError();
+}
+
+// ===================================================================== lightmap_bake
+// Reference raytracer.c:722-784: every triangle, in slot order, rasterises its UV footprint into the lightmap; each
+// covered texel gets `samples` cosine-weighted cast_ray estimates from the interpolated surface point; a texel covered by
+// several triangles keeps the LAST one's value.  Here: (1) an ownership pass finds that last triangle per texel
+// (atomicMax over slots — same coverage arithmetic, f32, no contraction), (2) owned texels are compacted into jobs,
+// (3) every (job, sample) is a path of the same wavefront as the renderer — its first ray comes from the texel instead
+// of the camera — and (4) the cosine-weighted sum is taken per job in sample order.  Per-(texel, sample) seeds
+// (rt_seed.h) replace the reference's two sequential generator streams, as for the renderer.
+struct LightmapParams {
+  int      width, height, samples;
+  int     *owner;          // [W*H] slot of the last covering triangle, -1 = none
+  unsigned *jobs;          // [n_jobs] texel index
+  unsigned *n_jobs;
+  float   *sums;           // [n_jobs][3] running cosine-weighted sums
+  float   *cosw;           // [path] cosine of the sample's first direction (0: no direction found)
+};
+
+// barycentric weights of texel (x, y) in UV triangle `slot` exactly as raytracer.c:733-745 computes them
+__device__ __forceinline__ bool lightmap_weights(const SceneDev &sc, int slot, float W, float H, float px, float py,
+                                                 float &w0, float &w1, float &w2) {
+  const float4 r4 = __ldg(sc.tri_rec + (size_t)slot * 7 + 4), r5 = __ldg(sc.tri_rec + (size_t)slot * 7 + 5);
+  const float p0x = r4.z * W, p0y = r4.w * H, p1x = r5.x * W, p1y = r5.y * H, p2x = r5.z * W, p2y = r5.w * H;
+  const float denom = (p1y - p2y) * (p0x - p2x) + (p2x - p1x) * (p0y - p2y);
+  w0 = ((p1y - p2y) * (px - p2x) + (p2x - p1x) * (py - p2y)) / denom;
+  w1 = ((p2y - p0y) * (px - p2x) + (p0x - p2x) * (py - p2y)) / denom;
+  w2 = 1.0f - w0 - w1;
+  return w0 >= -RT_EPS && w1 >= -RT_EPS && w2 >= -RT_EPS;
+}
+
+// one block per triangle slot: the texels of its UV bounding box (raytracer.c:728-731: float products truncated to i32)
+__global__ void __launch_bounds__(128)
+rt_lightmap_owner_kernel(const SceneDev sc, const LightmapParams L) {
+  const int slot = blockIdx.x;
+  const float W = (float)L.width, H = (float)L.height;
+  const float4 r4 = __ldg(sc.tri_rec + (size_t)slot * 7 + 4), r5 = __ldg(sc.tri_rec + (size_t)slot * 7 + 5);
+  const float ax = r4.z, ay = r4.w, bx = r5.x, by = r5.y, cx = r5.z, cy = r5.w;
+  const int min_x = (int)(sel_min(ax, sel_min(bx, cx)) * W), max_x = (int)(sel_max(ax, sel_max(bx, cx)) * W);
+  const int min_y = (int)(sel_min(ay, sel_min(by, cy)) * H), max_y = (int)(sel_max(ay, sel_max(by, cy)) * H);
+  // texels outside the lightmap are not stored (the reference writes out of bounds): clip the box
+  const int x0 = min_x < 0 ? 0 : min_x, x1 = max_x >= L.width ? L.width - 1 : max_x;
+  const int y0 = min_y < 0 ? 0 : min_y, y1 = max_y >= L.height ? L.height - 1 : max_y;
+  if (x1 < x0 || y1 < y0) return;
+  const int bw = x1 - x0 + 1, n = bw * (y1 - y0 + 1);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int x = x0 + i % bw, y = y0 + i / bw;
+    float w0, w1, w2;
+    if (lightmap_weights(sc, slot, W, H, (float)x, (float)y, w0, w1, w2)) atomicMax(&L.owner[y * L.width + x], slot);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+rt_lightmap_jobs_kernel(const LightmapParams L) {
+  const unsigned n = (unsigned)(L.width * L.height), lane = threadIdx.x & 31u;
+  const unsigned n_round = (n + 31u) & ~31u;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+    const bool owned = i < n && L.owner[i] >= 0;
+    const unsigned pos = warp_append(L.n_jobs, owned, lane);
+    if (owned) L.jobs[pos] = i;
+  }
+}
+
+// common.h:30-42 with the generator state in a register; the final scale is a DOUBLE division narrowed to f32
+__device__ __forceinline__ V3 lightmap_rand_vec3(uint32_t &state) {
+  for (;;) {
+    V3 p;
+    p.x = rt_rand_f32(&state) * 2.0f + -1.0f;
+    p.y = rt_rand_f32(&state) * 2.0f + -1.0f;
+    p.z = rt_rand_f32(&state) * 2.0f + -1.0f;
+    const float lensq = dot3(p, p);
+    if (RT_EPS < lensq && lensq <= 1) return scale3(p, (float)(1.0 / (double)__fsqrt_rn(lensq)));
+  }
+}
+
+// first ray of path (job, sample): raytracer.c:747-772
+__global__ void __launch_bounds__(256)
+rt_lightmap_raygen_kernel(const __grid_constant__ StageParams P, const LightmapParams L, unsigned n_jobs) {
+  const SceneDev &sc = P.scene;
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned n = n_jobs * (unsigned)P.n_samples, n_round = (n + 31u) & ~31u;
+  const float W = (float)L.width, H = (float)L.height;
+  for (unsigned path = blockIdx.x * blockDim.x + threadIdx.x; path < n_round; path += gridDim.x * blockDim.x) {
+    bool shoot = false;
+    V3 o = mk3(0, 0, 0), d = mk3(0, 0, 0);
+    uint32_t rng = 0;
+    if (path < n) {
+      const unsigned job = path / (unsigned)P.n_samples;
+      const int s = P.sample0 + (int)(path - job * (unsigned)P.n_samples);
+      const unsigned texel = L.jobs[job];
+      const int slot = L.owner[texel];
+      const int x = (int)(texel % (unsigned)L.width), y = (int)(texel / (unsigned)L.width);
+      float w0, w1, w2;
+      lightmap_weights(sc, slot, W, H, (float)x, (float)y, w0, w1, w2);
+      const float *soa = sc.tri_soa + slot;
+      const size_t N = (size_t)sc.n_slots;
+      const V3 position = mk3(soa[0] * w0 + soa[N] * w1 + soa[2 * N] * w2,
+                              soa[3 * N] * w0 + soa[4 * N] * w1 + soa[5 * N] * w2,
+                              soa[6 * N] * w0 + soa[7 * N] * w1 + soa[8 * N] * w2);
+      const float4 *rec = sc.tri_rec + (size_t)slot * 7;
+      const float4 r0 = __ldg(rec), r1 = __ldg(rec + 1), r2 = __ldg(rec + 2);
+      const V3 normal = mk3(r0.w * w0 + r1.z * w1 + r2.y * w2, r1.x * w0 + r1.w * w1 + r2.z * w2, r1.y * w0 + r2.x * w1 + r2.w * w2);
+      o = add3(position, scale3(normal, RT_EPS));
+      uint32_t dir_state = rt_path_seed(texel, (uint32_t)s, P.user_seed ^ RT_LIGHTMAP_DIR_SALT);
+      rng = rt_path_seed(texel, (uint32_t)s, P.user_seed);
+      float cosine = 0;
+      for (int tries = 0; tries < RT_LIGHTMAP_MAX_TRIES; tries++) {
+        d = lightmap_rand_vec3(dir_state);
+        cosine = dot3(d, normal);
+        if (cosine > 0) break;
+        cosine = 0;
+      }
+      shoot = cosine > 0;
+      L.cosw[path] = cosine;
+      if (!shoot) P.q.rad[path] = make_float4(0, 0, 0, 0);
+    }
+    const unsigned pos = warp_append(&P.q.counts[Q_RAYS], shoot, lane);
+    if (shoot) {
+      P.q.ray_a[pos] = make_float4(o.x, o.y, o.z, d.x);
+      P.q.ray_b[pos] = make_float4(d.y, d.z, __uint_as_float(path), __uint_as_float(rng));
+    }
+  }
+}
+
+// raytracer.c:773: accumulated += cast_ray(...) * cos, in sample order
+__global__ void __launch_bounds__(256)
+rt_lightmap_accumulate_kernel(const __grid_constant__ StageParams P, const LightmapParams L, unsigned n_jobs, int first_chunk) {
+  for (unsigned job = blockIdx.x * blockDim.x + threadIdx.x; job < n_jobs; job += gridDim.x * blockDim.x) {
+    V3 sum = first_chunk ? mk3(0, 0, 0) : mk3(L.sums[3 * job], L.sums[3 * job + 1], L.sums[3 * job + 2]);
+    const size_t base = (size_t)job * (size_t)P.n_samples;
+    for (int s = 0; s < P.n_samples; s++) {
+      const float c = L.cosw[base + s];
+      if (!(c > 0)) continue;
+      const float4 v = P.q.rad[base + s];
+      sum = add3(sum, scale3(mk3(v.x, v.y, v.z), c));
+    }
+    L.sums[3 * job] = sum.x; L.sums[3 * job + 1] = sum.y; L.sums[3 * job + 2] = sum.z;
+  }
+}
+
+// raytracer.c:777-779: the UN-SCALED f32 goes into the u8 (saturating here; C leaves out-of-range undefined)
+__global__ void __launch_bounds__(256)
+rt_lightmap_store_kernel(const LightmapParams L, unsigned n_jobs, unsigned char *pixels, int stride, int components, float *values) {
+  for (unsigned job = blockIdx.x * blockDim.x + threadIdx.x; job < n_jobs; job += gridDim.x * blockDim.x) {
+    const unsigned texel = L.jobs[job];
+    const int x = (int)(texel % (unsigned)L.width), y = (int)(texel / (unsigned)L.width);
+    unsigned char *dst = pixels + (size_t)components * (size_t)(x + y * stride);
+    for (int c = 0; c < 3; c++) {
+      const float v = L.sums[3 * job + c] / (float)L.samples;
+      if (values) values[3 * (size_t)texel + c] = v;
+      dst[c] = !(v == v) ? 0 : (v <= 0 ? 0 : (v >= 255 ? 255 : (unsigned char)v));
+    }
+  }
+}
+
+size_t rt_lightmap_workspace_bytes(int width, int height) {
+  const size_t n = (size_t)width * (size_t)height;
+  return ((n * (sizeof(int) + sizeof(unsigned) + 3 * sizeof(float)) + 256 + 255) & ~(size_t)255);
+}
+
+// `scratch` holds owner / jobs / sums (rt_lightmap_workspace_bytes), `workspace` the path queues plus one f32 per path.
+int rt_launch_lightmap(const SceneDev &scene, int width, int height, int samples, int max_bounces, uint32_t user_seed,
+                       unsigned char *d_pixels, int stride, int components, float *d_values, int *d_owner_out,
+                       void *scratch, int sm_count, void *workspace, size_t workspace_bytes, cudaStream_t stream,
+                       int *n_launches, unsigned *n_jobs_out) {
+  size_t level_bytes = 0;
+  int dev = 0;
+  if (int e = trace_launch_setup(scene, &dev, &level_bytes)) return e;
+  const size_t n_texels = (size_t)width * (size_t)height;
+  LightmapParams L{};
+  L.width = width; L.height = height; L.samples = samples;
+  char *sp = static_cast<char *>(scratch);
+  L.n_jobs = reinterpret_cast<unsigned *>(sp); sp += 256;
+  L.owner = reinterpret_cast<int *>(sp);       sp += n_texels * sizeof(int);
+  L.jobs = reinterpret_cast<unsigned *>(sp);   sp += n_texels * sizeof(unsigned);
+  L.sums = reinterpret_cast<float *>(sp);
+  cudaMemsetAsync(L.n_jobs, 0, 256, stream);
+  cudaMemsetAsync(L.owner, 0xff, n_texels * sizeof(int), stream);
+  const unsigned flat_grid = (unsigned)(sm_count * 8);
+  rt_lightmap_owner_kernel<<<(unsigned)scene.n_slots, 128, 0, stream>>>(scene, L);
+  rt_lightmap_jobs_kernel<<<flat_grid, 256, 0, stream>>>(L);
+  int launches = 2;
+  unsigned n_jobs = 0;
+  cudaMemcpyAsync(&n_jobs, L.n_jobs, sizeof n_jobs, cudaMemcpyDeviceToHost, stream);
+  if (cudaError_t e = cudaStreamSynchronize(stream)) return (int)e;
+  if (n_jobs_out) *n_jobs_out = n_jobs;
+  if (d_owner_out) cudaMemcpyAsync(d_owner_out, L.owner, n_texels * sizeof(int), cudaMemcpyDeviceToDevice, stream);
+  if (n_jobs == 0 || samples < 1 || max_bounces < 1) { if (n_launches) *n_launches += launches; return (int)cudaGetLastError(); }
+
+  StageParams P{};
+  P.scene = scene;
+  P.width = width; P.height = height;
+  P.max_bounces = max_bounces;
+  P.user_seed = user_seed;
+  const size_t cb = counts_bytes(max_bounces);
+  const size_t per_path = RT_PATH_BYTES + sizeof(float);
+  if (workspace_bytes < cb + (size_t)n_jobs * per_path) return (int)cudaErrorMemoryAllocation;
+  size_t cap = (workspace_bytes - cb) / per_path;
+  size_t fit = chunk_samples(n_jobs, samples, 0);
+  if (fit > cap / n_jobs) fit = cap / n_jobs;
+  const int chunk = (int)fit;
+  cap = (size_t)chunk * n_jobs;
+  bind_queues(P.q, static_cast<char *>(workspace), cb, cap);
+  L.cosw = reinterpret_cast<float *>(static_cast<char *>(workspace) + cb + cap * RT_PATH_BYTES);
+  const unsigned trace_grid = (unsigned)(sm_count * g_trace_blocks_per_sm[dev]);
+  for (int s0 = 0; s0 < samples; s0 += chunk) {
+    const int S = samples - s0 < chunk ? samples - s0 : chunk;
+    P.sample0 = s0; P.n_samples = S;
+    P.n_paths = n_jobs * (unsigned)S;
+    cudaMemsetAsync(P.q.counts, 0, cb, stream);
+    rt_lightmap_raygen_kernel<<<flat_grid, 256, 0, stream>>>(P, L, n_jobs);
+    launches++;
+    for (int b = 0; b < max_bounces; b++) {
+      P.bounce = b;
+      rt_trace_kernel<false><<<trace_grid, RT_BLOCK, level_bytes, stream>>>(P);
+      rt_miss_kernel<<<flat_grid, 256, 0, stream>>>(P);
+      rt_shade_kernel<<<flat_grid, 256, 0, stream>>>(P);
+      launches += 3;
+    }
+    rt_lightmap_accumulate_kernel<<<flat_grid, 256, 0, stream>>>(P, L, n_jobs, s0 == 0);
+    launches++;
+  }
+  rt_lightmap_store_kernel<<<flat_grid, 256, 0, stream>>>(L, n_jobs, d_pixels, stride, components, d_values);
+  launches++;
   if (n_launches) *n_launches += launches;
   return (int)cudaGetLastError();
 }

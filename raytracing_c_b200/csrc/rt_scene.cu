@@ -143,6 +143,7 @@ static int h2d(Device &d, DeviceScene &ds, void *dst, const void *src, size_t n)
 struct HostScene {
   std::vector<float>       nodes;
   std::vector<float4>      tri_pos, records;
+  std::vector<float>       tri_soa;
   std::vector<MaterialDev> materials;
   std::vector<const Image *> images;
   int   env_slot = -1;
@@ -184,6 +185,15 @@ static int flatten(const Scene *scene, HostScene &hs) {
     hs.tri_pos[(size_t)s * 3 + 0] = make_float4(px[0][s], px[1][s], px[2][s], e1[0]);
     hs.tri_pos[(size_t)s * 3 + 1] = make_float4(e1[1], e1[2], e2[0], e2[1]);
     hs.tri_pos[(size_t)s * 3 + 2] = make_float4(e2[2], 0.0f, 0.0f, 0.0f);
+  }
+
+  // the vertex arrays as they are (lightmap_bake interpolates positions from the three vertices, raytracer.c:749-753)
+  hs.tri_soa.resize((size_t)n_slots * 9);
+  {
+    const float *arrays[9] = { scene->triangles.x[0], scene->triangles.x[1], scene->triangles.x[2],
+                               scene->triangles.y[0], scene->triangles.y[1], scene->triangles.y[2],
+                               scene->triangles.z[0], scene->triangles.z[1], scene->triangles.z[2] };
+    for (int a = 0; a < 9; a++) memcpy(hs.tri_soa.data() + (size_t)a * (size_t)n_slots, arrays[a], (size_t)n_slots * sizeof(float));
   }
 
   // materials / textures, de-duplicated by host pointer
@@ -279,7 +289,7 @@ static int make_events(DeviceScene &ds) {
 //   [ environment texels | nodes | tri_pos | tri_rec | materials ]  [ texture table ] [ nodes_rel | tri_rel ] [ other texels ]
 // The first bracket is what every ray re-reads; the persisting window (set_l2_window) starts there.
 struct ArenaLayout {
-  size_t env, nodes, tri_pos, tri_rec, materials, hot_end, table, nodes_rel, tri_rel, texels_begin, total;
+  size_t env, nodes, tri_pos, tri_rec, materials, tri_soa, hot_end, table, nodes_rel, tri_rel, texels_begin, total;
   std::vector<size_t> texel_off;     // per image slot
 };
 
@@ -296,6 +306,7 @@ static ArenaLayout layout_of(const HostScene &hs) {
   L.tri_pos = off;   off = align256(off + hs.tri_pos.size() * sizeof(float4));
   L.tri_rec = off;   off = align256(off + hs.records.size() * sizeof(float4));
   L.materials = off; off = align256(off + hs.materials.size() * sizeof(MaterialDev));
+  L.tri_soa = off;   off = align256(off + hs.tri_soa.size() * sizeof(float));
   L.hot_end = off;
   L.table = off;     off = align256(off + hs.images.size() * sizeof(TextureDev) + 16);
   L.nodes_rel = off; off = align256(off + hs.nodes.size() * sizeof(float));
@@ -315,6 +326,7 @@ static void bind_arena(char *base, const ArenaLayout &L, const HostScene &hs, De
   ds.dev.tri_pos   = reinterpret_cast<const float4 *>(base + L.tri_pos);
   ds.dev.tri_rec   = reinterpret_cast<const float4 *>(base + L.tri_rec);
   ds.dev.materials = reinterpret_cast<const MaterialDev *>(base + L.materials);
+  ds.dev.tri_soa   = reinterpret_cast<const float *>(base + L.tri_soa);
   ds.dev.textures  = reinterpret_cast<const TextureDev *>(base + L.table);
   ds.dev.nodes_rel = reinterpret_cast<float *>(base + L.nodes_rel);
   ds.dev.tri_rel   = reinterpret_cast<float4 *>(base + L.tri_rel);
@@ -343,6 +355,7 @@ static int upload_primary(Device &d, const HostScene &hs, const ArenaLayout &L, 
   if (h2d(d, ds, base + L.tri_pos, hs.tri_pos.data(), hs.tri_pos.size() * sizeof(float4))) return 1;
   if (h2d(d, ds, base + L.tri_rec, hs.records.data(), hs.records.size() * sizeof(float4))) return 1;
   if (h2d(d, ds, base + L.materials, hs.materials.data(), hs.materials.size() * sizeof(MaterialDev))) return 1;
+  if (h2d(d, ds, base + L.tri_soa, hs.tri_soa.data(), hs.tri_soa.size() * sizeof(float))) return 1;
   if (h2d(d, ds, base + L.table, table.data(), table.size() * sizeof(TextureDev))) return 1;
   CUDA_TRY(cudaEventRecord(ds.geom_ready, d.copy));
   // texels: raw rows go up as they are (3 B per texel for RGB8); the RGBA8 layout the samplers read (one 32-bit load

@@ -130,7 +130,7 @@ def image_view(pixels: np.ndarray) -> Image:
     return im
 
 
-def set_options(user_seed: int = 0, sample_begin: int = 0, sample_end: int = 0, slice_samples: int = 64,
+def set_options(user_seed: int = 0, sample_begin: int = 0, sample_end: int = 0, slice_samples: int = 0,
                 keep_hit_ids: bool = False, sample_range_set: bool = False, split_mode: int = 0, reduce_mode: int = 0,
                 pixel_rank: int = 0, pixel_world: int = 0) -> None:
     opt = GPUOptions(user_seed, sample_begin, sample_end, slice_samples, int(keep_hit_ids), int(sample_range_set),
@@ -181,6 +181,25 @@ def denoise(src: np.ndarray, n_threads: int = 1) -> np.ndarray:
     if gpu.rt_gpu_last_status() != 0:
         raise RuntimeError("libraytracer_gpu: " + gpu.rt_gpu_last_error().decode())
     return dst
+
+
+def lightmap_bake(loaded: LoadedScene, width: int, height: int, samples: int, out: Optional[np.ndarray] = None,
+                  want_values: bool = False):
+    """raytracer.h's lightmap_bake (reference raytracer.c:722-784) on the GPU.  Returns the u8 lightmap, or — with
+    want_values — a dict with the f32 values before the u8 store and the owning triangle slot per texel."""
+    gpu = gpu_lib()
+    register_callbacks(loaded)
+    pixels = out if out is not None else np.zeros((height, width, 3), dtype=np.uint8)
+    im = image_view(pixels)
+    if not want_values:
+        gpu.lightmap_bake(C.byref(im), C.byref(loaded.scene), samples)
+        if gpu.rt_gpu_last_status() != 0:
+            raise RuntimeError("libraytracer_gpu: " + gpu.rt_gpu_last_error().decode())
+        return pixels
+    values = np.zeros((height, width, 3), dtype=np.float32)
+    owner = np.full((height, width), -1, dtype=np.int32)
+    gpu_check(gpu.rt_gpu_lightmap_bake(C.byref(im), C.byref(loaded.scene), samples, values.ctypes.data, owner.ctypes.data))
+    return dict(pixels=pixels, values=values, owner=owner)
 
 
 def read_accum(width: int, height: int) -> np.ndarray:

@@ -32,6 +32,11 @@ class OracleOptions(C.Structure):
                 ("counters", C.c_uint64 * 8), ("pixel_mask", C.c_void_p)]
 
 
+class OracleLightmapOptions(C.Structure):
+    _fields_ = [("seed_mode", C.c_int32), ("user_seed", C.c_uint32), ("dir_state", C.c_uint32), ("shader_state", C.c_uint32),
+                ("values", C.c_void_p), ("owner", C.c_void_p), ("texels_written", C.c_int64)]
+
+
 def build_oracle() -> None:
     out = subprocess.run(["make", "-C", ORACLE_DIR, "all"], capture_output=True, text=True)
     if out.returncode:
@@ -61,6 +66,8 @@ def lib() -> C.CDLL:
         o.oracle_sample_background.argtypes = [C.c_void_p, Vec3]
         o.oracle_sample_background.restype = Vec3
         o.oracle_shader_random_state.restype = C.POINTER(C.c_uint32)
+        o.oracle_lightmap_bake.argtypes = [C.POINTER(Image), C.POINTER(Scene), isize, C.POINTER(OracleLightmapOptions)]
+        o.oracle_lightmap_bake.restype = None
         _lib = o
     return _lib
 
@@ -121,3 +128,19 @@ def resolve(accum: np.ndarray, samples: int) -> np.ndarray:
     out = np.zeros(accum.shape, dtype=np.uint8)
     lib().oracle_resolve(accum.ctypes.data, accum.size // 3, samples, out.ctypes.data)
     return out
+
+
+def lightmap_bake(loaded, width, height, samples, seed_mode=SEED_PER_SAMPLE, user_seed=0, dir_state=0, shader_state=0):
+    """oracle_lightmap_bake (raytracer.c:722-784): returns the u8 lightmap, the f32 values before the u8 store,
+    the slot that wrote each texel last (-1 = untouched) and the number of stores."""
+    from raytracing_c_b200.driver import image_view
+    pixels = np.zeros((height, width, 3), dtype=np.uint8)
+    values = np.zeros((height, width, 3), dtype=np.float32)
+    owner = np.full((height, width), -1, dtype=np.int32)
+    im = image_view(pixels)
+    opt = OracleLightmapOptions()
+    opt.seed_mode, opt.user_seed, opt.dir_state, opt.shader_state = seed_mode, user_seed, dir_state, shader_state
+    opt.values, opt.owner = values.ctypes.data, owner.ctypes.data
+    lib().oracle_lightmap_bake(C.byref(im), C.byref(loaded.scene), samples, C.byref(opt))
+    return dict(pixels=pixels, values=values, owner=owner, stores=int(opt.texels_written),
+                dir_state=int(opt.dir_state), shader_state=int(opt.shader_state))

@@ -109,3 +109,21 @@ def denoise(src: np.ndarray) -> np.ndarray:
     a, b = image_view(src), image_view(dst)
     lib().denoise_image(C.byref(a), C.byref(b), 1)
     return dst
+
+
+def lightmap_bake(loaded, width, height, samples, dir_state=0, shader_state=0):
+    """The reference's own lightmap_bake (raytracer.c:722-784), both generator copies started where asked.
+    It writes texels at x == width / y == height when a UV is exactly 1.0 (out of bounds): the image handed to it
+    has 8 spare columns (stride) and 8 spare rows for those; the in-range region is returned."""
+    from raytracing_c_b200.driver import image_view
+    r = lib()
+    r.ref_rt_random_state.restype = C.POINTER(C.c_uint32)
+    r.lightmap_bake.argtypes = [C.POINTER(Image), C.c_void_p, isize]
+    r.lightmap_bake.restype = None
+    padded = np.zeros((height + 8, width + 8, 3), dtype=np.uint8)
+    im = image_view(padded)
+    im.width, im.height, im.stride = width, height, width + 8
+    r.ref_rt_random_state()[0] = dir_state
+    r.ref_random_state()[0] = shader_state
+    r.lightmap_bake(C.byref(im), C.byref(loaded.scene), samples)
+    return np.ascontiguousarray(padded[:height, :width])

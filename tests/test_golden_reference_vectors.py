@@ -67,3 +67,32 @@ def test_texture_and_environment_match_reference():
         assert np.array_equal(got, ARRAYS["background_out"])
     finally:
         loaded.close()
+
+
+@pytest.mark.parametrize("case", sorted(META["lightmap_cases"]))
+def test_lightmap_bake_matches_reference(case):
+    """oracle_lightmap_bake in the reference's sequential seed mode against the reference's own lightmap_bake
+    (raytracer.c:722-784): same u8 lightmap, overlapping triangles and out-of-range texels included."""
+    cfg = META["lightmap_cases"][case]
+    loaded = load(cfg["model"], emission=Vec3(*cfg["emission"]))
+    try:
+        got = oracle_ffi.lightmap_bake(loaded, cfg["width"], cfg["height"], cfg["samples"], seed_mode=oracle_ffi.SEED_REFERENCE,
+                                       dir_state=cfg["dir_state"], shader_state=cfg["shader_state"])
+        want = ARRAYS["lightmap/" + case]
+        assert (want > 0).sum() > 100 and got["stores"] > (got["owner"] >= 0).sum()      # texels are overwritten: order matters
+        assert np.array_equal(got["pixels"], want)
+    finally:
+        loaded.close()
+
+
+def test_lightmap_per_sample_seeding_is_order_free():
+    """The per-(texel, sample) seeding rule the GPU shares: a texel's value depends only on the LAST triangle that
+    covers it, so baking is independent of how the work is scheduled."""
+    loaded = load("spheres.glb", emission=Vec3(30.0, 20.0, 10.0))
+    try:
+        a = oracle_ffi.lightmap_bake(loaded, 40, 40, 2)
+        b = oracle_ffi.lightmap_bake(loaded, 40, 40, 2, dir_state=555, shader_state=777)     # stream states are ignored
+        assert np.array_equal(a["values"], b["values"]) and np.array_equal(a["pixels"], b["pixels"])
+        assert (a["owner"] >= 0).sum() > 500 and a["values"].max() > 1.0
+    finally:
+        loaded.close()

@@ -12,6 +12,8 @@ stand-in — and records small input/output vectors of the hot path:
   hash12_xy / hash12_out      hash12x8 lane 0 (raytracer.c:584)
   bilinear_uv / bilinear_out  sample_texture_bilinear (driver.c:49) on the procedural environment
   background_dir / _out       sample_background (driver.c:95)
+  lightmap/<case>             lightmap_bake (raytracer.c:722), u8 image, both generator copies started from the
+                              recorded states (the sequential "reference" seed mode)
 
 quad.obj and fov_test.obj are absent from bvh_sha256: the reference's builder has undefined
 behaviour on them.
@@ -43,6 +45,13 @@ RADIANCE_CASES = {
     "sheen_injected_16x16x4": ("sheen.glb", 16, 16, 4, 8, {"sheen": 1.0, "sheen_tint": 0.5}, None),
     "tower_16x16x2": ("tower.obj", 16, 16, 2, 8, {}, dict(eye=(0.0, 12.5, 40.0), target=(0.0, 12.5, 0.0))),
     "spheres_2bounce_16x16x2": ("spheres.glb", 16, 16, 2, 2, {"anisotropic_strength": 0.6}, None),
+}
+
+
+LIGHTMAP_CASES = {
+    # name: (model, width, height, samples, emission override, dir_state, shader_state)
+    "tower_64x48x3": ("tower.obj", 64, 48, 3, (30.0, 20.0, 10.0), 123, 7),
+    "spheres_48x48x2": ("spheres.glb", 48, 48, 2, (30.0, 20.0, 10.0), 99, 5),
 }
 
 
@@ -81,6 +90,11 @@ def main():
         arrays["radiance/" + name] = ref_ffi.cast_rays_per_sample(loaded, w, h, spp, bounces)
         loaded.close()
 
+    for name, (model, w, h, n, emission, dir_state, shader_state) in LIGHTMAP_CASES.items():
+        loaded = load_ref(model, {"emission": Vec3(*emission)})
+        arrays["lightmap/" + name] = ref_ffi.lightmap_bake(loaded, w, h, n, dir_state=dir_state, shader_state=shader_state)
+        loaded.close()
+
     rng = np.random.default_rng(2026)
     img = rng.integers(0, 256, size=(40, 48, 3), dtype=np.uint8)
     img[:20] = (img[:20] // 48) * 48
@@ -107,7 +121,9 @@ def main():
 
     np.savez_compressed(os.path.join(OUT, "reference_vectors.npz"), **arrays)
     meta = {"generator": "tools/make_golden.py", "source": "oracle/_ref/libref.so = /root/reference/{raytracer,scene,denoiser,driver}.c unmodified + oracle/codin_shim",
-            "bvh": digests, "radiance_cases": {k: dict(model=v[0], width=v[1], height=v[2], spp=v[3], bounces=v[4], override=v[5], camera=v[6]) for k, v in RADIANCE_CASES.items()}}
+            "bvh": digests, "radiance_cases": {k: dict(model=v[0], width=v[1], height=v[2], spp=v[3], bounces=v[4], override=v[5], camera=v[6]) for k, v in RADIANCE_CASES.items()},
+            "lightmap_cases": {k: dict(model=v[0], width=v[1], height=v[2], samples=v[3], emission=list(v[4]), dir_state=v[5], shader_state=v[6])
+                               for k, v in LIGHTMAP_CASES.items()}}
     json.dump(meta, open(os.path.join(OUT, "reference_vectors.json"), "w"), indent=1)
     print("wrote", OUT, {k: v.shape for k, v in arrays.items()})
 

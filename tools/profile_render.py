@@ -32,7 +32,6 @@ loaded = driver.load_scene(os.path.join(ROOT, "assets", "models", args.model))
 driver.register_callbacks(loaded)
 scene = C.byref(loaded.scene)
 gpu_check(gpu.rt_gpu_scene_upload(scene))
-driver.set_options(slice_samples=args.spp)      # chunking is then bounded by RT_GPU_CHUNK_PATHS alone
 W, H = args.width, args.height
 accum = torch.zeros(W * H * 3, dtype=torch.float32, device="cuda")
 pixels = torch.zeros(W * H * 3, dtype=torch.uint8, device="cuda")
