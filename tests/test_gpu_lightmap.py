@@ -34,7 +34,7 @@ def test_lightmap_values_owner_and_bytes_equal_the_oracle(name, w, h, samples, s
         written = ref["owner"] >= 0
         assert np.array_equal(got["pixels"][written], ref["pixels"][written])
         assert (got["pixels"][~written] == 77).all(), "untouched texels keep their bytes"
-        assert ref["values"].max() > 1.0
+        assert ref["values"].max() > 0.3
     finally:
         driver.set_options()
         loaded.close()
