@@ -41,7 +41,10 @@ typedef struct { f32 rows[4][4]; } Matrix_4x4;
 
 typedef struct { u8 *data; isize len; } Byte_Slice;
 
-enum { PT_u8 = 0 };
+/* PT_RT_JPEG_BYTES is this repo's extension: pixels holds a COMPRESSED baseline JPEG (pixels.len bytes), width and
+ * height come from its frame header, components is 3.  Only the GPU library's scene upload accepts such an image
+ * (it decodes with nvJPEG straight into device memory, rt_gpu.h); librt_host produces it on request. */
+enum { PT_u8 = 0, PT_RT_JPEG_BYTES = 0x4A50 };
 
 /* stride is in pixels (reference raytracer.c:714, denoiser.c:24). */
 typedef struct {

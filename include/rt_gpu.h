@@ -97,6 +97,8 @@ enum {
 int rt_gpu_read_accum(f32 *out, isize n_floats);       /* W*H*3 sums of cast_ray, pre-division */
 int rt_gpu_read_hit_ids(i32 *out, isize n_pixels);     /* padded slot or -1 */
 int rt_gpu_read_counters(u64 out[8]);
+/* RGBA8 texels of texture `slot` of a resident scene (first device); out may be NULL to query the size */
+int rt_gpu_read_texture(Scene const *scene, i32 slot, u8 *out, isize *width, isize *height);
 /* the library's own 16-slot device counter block (first device): slots [0..8) as above, [8] rays whose whole walk
  * was the root-union test, [9] primary rays; pass it as d_counters to the device-level calls to get [8..16) filled */
 int rt_gpu_counters_buffer(u64 **d_counters_out);

@@ -118,7 +118,7 @@ GPU_EXPORTS = [
     "rt_gpu_scene_device_bytes", "rt_gpu_scene_upload_bytes",
     "rt_gpu_register_pbr_shader", "rt_gpu_register_background", "rt_gpu_pbr_shader_proc", "rt_gpu_background_proc",
     "rt_gpu_scene_upload", "rt_gpu_scene_release", "rt_gpu_set_options", "rt_gpu_get_options",
-    "rt_gpu_read_accum", "rt_gpu_read_hit_ids", "rt_gpu_read_counters", "rt_gpu_counters_buffer", "rt_gpu_counters_reset",
+    "rt_gpu_read_accum", "rt_gpu_read_hit_ids", "rt_gpu_read_counters", "rt_gpu_counters_buffer", "rt_gpu_counters_reset", "rt_gpu_read_texture",
     "rt_gpu_read_counters_ex", "rt_gpu_last_launches",
     "rt_gpu_last_kernel_ms", "rt_gpu_stage_profile_enable", "rt_gpu_stage_profile_read", "rt_gpu_stage_profile_read_bounces",
     "rt_gpu_render_accum_device", "rt_gpu_resolve_device", "rt_gpu_denoise_device",
@@ -128,7 +128,7 @@ HOST_EXPORTS = [
     "scene_init", "scene_destroy", "rt_load_model_file", "rt_model_free", "rt_camera_default", "rt_camera_look_at",
     "rt_image_decode", "rt_load_texture", "rt_image_free", "rt_image_alloc", "rt_generate_background",
     "rt_save_image", "rt_save_png", "rt_save_qoi", "rt_save_ppm", "rt_host_last_error",
-    "rt_host_set_buffer_allocator", "rt_host_buffer_alloc", "rt_host_buffer_free",
+    "rt_host_set_buffer_allocator", "rt_host_buffer_alloc", "rt_host_buffer_free", "rt_host_defer_jpeg_decode",
 ]
 
 
@@ -173,6 +173,8 @@ def host_lib() -> C.CDLL:
         lib.rt_host_last_error.restype = C.c_char_p
         lib.rt_host_set_buffer_allocator.argtypes = [C.c_void_p, C.c_void_p]
         lib.rt_host_set_buffer_allocator.restype = None
+        lib.rt_host_defer_jpeg_decode.argtypes = [C.c_bool]
+        lib.rt_host_defer_jpeg_decode.restype = None
         _host = lib
     return _host
 
@@ -225,6 +227,7 @@ def gpu_lib() -> C.CDLL:
         lib.rt_gpu_read_counters.argtypes = [C.c_void_p]
         lib.rt_gpu_counters_buffer.argtypes = [C.POINTER(C.c_void_p)]
         lib.rt_gpu_read_counters_ex.argtypes = [C.c_void_p]
+        lib.rt_gpu_read_texture.argtypes = [C.POINTER(Scene), C.c_int32, C.c_void_p, C.POINTER(isize), C.POINTER(isize)]
         lib.rt_gpu_last_kernel_ms.restype = C.c_double
         lib.rt_gpu_stage_profile_enable.argtypes = [C.c_int32]
         lib.rt_gpu_stage_profile_enable.restype = None

@@ -224,6 +224,7 @@ void rt_gpu_shutdown(void) {
   std::lock_guard<std::mutex> lock(g_mutex);
   nccl_shutdown();
   ipc_close_all();
+  jpeg_shutdown();
   for (Device &d : g.devs) release_device(d);
   std::vector<Shader_Proc> pbr = g.pbr_procs;
   std::vector<Background_Proc> bg = g.bg_procs;
@@ -431,6 +432,28 @@ int rt_gpu_read_hit_ids(i32 *out, isize n_pixels) {
     }
     CUDA_TRY(cudaSetDevice(g.devs[0].id));
   }
+  return 0;
+}
+
+// texels (RGBA8, tightly packed) of texture `slot` of a resident scene on the first device; slot order = first use by
+// the materials in triangle-slot order, the environment last unless a material uses it.  *width / *height are set;
+// out may be NULL to query the size, slot beyond the last returns non-zero.
+int rt_gpu_read_texture(Scene const *scene, i32 slot, u8 *out, isize *width, isize *height) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  if (g.devs.empty()) return fail("read_texture: not initialised");
+  Device &d = g.devs[0];
+  auto it = d.scenes.find(scene);
+  if (it == d.scenes.end()) return fail("read_texture: scene is not resident");
+  CUDA_TRY(cudaSetDevice(d.id));
+  CUDA_TRY(cudaStreamSynchronize(d.copy));
+  TextureDev table[64];
+  const char *tab = reinterpret_cast<const char *>(it->second.dev.textures);
+  const int n = it->second.n_textures;
+  if (slot < 0 || slot >= n || n > 64) return fail("read_texture: slot %d of %d", slot, n);
+  CUDA_TRY(cudaMemcpy(table, tab, (size_t)n * sizeof(TextureDev), cudaMemcpyDeviceToHost));
+  if (width) *width = table[slot].width;
+  if (height) *height = table[slot].height;
+  if (out) CUDA_TRY(cudaMemcpy(out, table[slot].texels, (size_t)table[slot].width * (size_t)table[slot].height * 4, cudaMemcpyDeviceToHost));
   return 0;
 }
 

@@ -255,8 +255,9 @@ static int flatten(const Scene *scene, HostScene &hs) {
     return fail("scene: Scene.background.proc was not registered with rt_gpu_register_background (or its Image is null)");
   hs.env_slot = texture_slot(static_cast<const Image *>(scene->background.data));
   for (size_t i = 0; i < hs.images.size(); i++)
-    if (hs.images[i]->components < 3 || !hs.images[i]->pixels.data || hs.images[i]->width < 1 || hs.images[i]->height < 1)
-      return fail("scene: texture %zu needs >= 3 u8 components and a non-empty pixel buffer", i);
+    if (hs.images[i]->components < 3 || !hs.images[i]->pixels.data || hs.images[i]->width < 1 || hs.images[i]->height < 1 ||
+        (hs.images[i]->pixel_type != PT_u8 && hs.images[i]->pixel_type != PT_RT_JPEG_BYTES))
+      return fail("scene: texture %zu needs >= 3 u8 components (or compressed JPEG bytes) and a non-empty pixel buffer", i);
 
   // union of the root's child boxes; all-zero padding slots (lo == hi) can never be entered (enter >= leave)
   for (int a = 0; a < 3; a++) { hs.root_lo[a] = INFINITY; hs.root_hi[a] = -INFINITY; }
@@ -338,6 +339,7 @@ static void bind_arena(char *base, const ArenaLayout &L, const HostScene &hs, De
   }
   ds.hot_base = base;
   ds.hot_bytes = L.hot_end;
+  ds.n_textures = (int)hs.images.size();
 }
 
 // device 0: over PCIe from the host buffers
@@ -363,7 +365,8 @@ static int upload_primary(Device &d, const HostScene &hs, const ArenaLayout &L, 
   // its first consumer.  Two raw staging blocks alternate, so the DMA of one image overlaps the repack of the previous.
   size_t raw_max = 0;
   for (const Image *im : hs.images) {
-    const size_t raw = (size_t)im->stride * (size_t)im->height * (size_t)im->components;
+    const size_t raw = im->pixel_type == PT_RT_JPEG_BYTES ? (size_t)im->width * (size_t)im->height * 3
+                                                          : (size_t)im->stride * (size_t)im->height * (size_t)im->components;
     if (raw > raw_max) raw_max = raw;
   }
   if (raw_max > d.texel_stage_bytes) {
@@ -375,10 +378,21 @@ static int upload_primary(Device &d, const HostScene &hs, const ArenaLayout &L, 
   for (size_t i = 0; i < hs.images.size(); i++) if ((int)i != hs.env_slot) order.push_back(i);
   for (size_t i : order) {
     const Image *im = hs.images[i];
-    const size_t raw = (size_t)im->stride * (size_t)im->height * (size_t)im->components;
-    if (h2d(d, ds, d.d_texel_stage, im->pixels.data, raw)) return 1;
-    int e = rt_launch_texel_repack(static_cast<const unsigned char *>(d.d_texel_stage), (int)im->width, (int)im->height,
-                                   (int)im->stride, im->components, reinterpret_cast<uchar4 *>(base + L.texel_off[i]), d.copy);
+    int e = 0;
+    if (im->pixel_type == PT_RT_JPEG_BYTES) {
+      // compressed on the host: nvJPEG decodes on the copy stream into the raw block (interleaved RGB), see rt_jpeg_gpu.cu
+      ds.h2d_bytes += (size_t)im->pixels.len;
+      if (jpeg_decode_device(im->pixels.data, (size_t)im->pixels.len, (int)im->width, (int)im->height,
+                             static_cast<unsigned char *>(d.d_texel_stage), d.copy))
+        return 1;
+      e = rt_launch_texel_repack(static_cast<const unsigned char *>(d.d_texel_stage), (int)im->width, (int)im->height,
+                                 (int)im->width, 3, reinterpret_cast<uchar4 *>(base + L.texel_off[i]), d.copy);
+    } else {
+      const size_t raw = (size_t)im->stride * (size_t)im->height * (size_t)im->components;
+      if (h2d(d, ds, d.d_texel_stage, im->pixels.data, raw)) return 1;
+      e = rt_launch_texel_repack(static_cast<const unsigned char *>(d.d_texel_stage), (int)im->width, (int)im->height,
+                                 (int)im->stride, im->components, reinterpret_cast<uchar4 *>(base + L.texel_off[i]), d.copy);
+    }
     if (e) return fail("texel repack launch failed: %s", cudaGetErrorString((cudaError_t)e));
   }
   CUDA_TRY(cudaEventRecord(ds.tex_ready, d.copy));

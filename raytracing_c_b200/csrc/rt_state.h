@@ -42,6 +42,7 @@ struct DeviceScene {
   cudaEvent_t tex_ready = nullptr;    // texels (incl. the environment) complete
   void  *hot_base = nullptr;          // head of the arena: environment texels, nodes, triangles (persisting-L2 window)
   size_t hot_bytes = 0;
+  int    n_textures = 0;
   Fingerprint fp;
 };
 
@@ -114,6 +115,10 @@ int scene_upload_all(const Scene *scene);                     // (re-)upload: de
 void scene_release_all(const Scene *scene);
 void release_device(Device &d);                               // everything the device owns (shutdown)
 void set_l2_window(Device &d, const DeviceScene &ds, cudaStream_t stream);
+
+// ---- rt_jpeg_gpu.cu
+int jpeg_decode_device(const unsigned char *bytes, size_t len, int width, int height, unsigned char *d_rgb, cudaStream_t stream);
+void jpeg_shutdown();
 
 // ---- rt_multi.cu
 int enable_peers();                                           // device 0 <-> every other device

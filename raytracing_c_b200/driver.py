@@ -69,6 +69,21 @@ def use_pinned_host_buffers(on: bool = True) -> None:
         host_lib().rt_host_set_buffer_allocator(None, None)
 
 
+def defer_jpeg_decode(on: bool = True) -> None:
+    """Models loaded from now on keep their JPEG textures compressed; rt_gpu_scene_upload decodes them on the device
+    (nvJPEG).  Such scenes can only be rendered by the GPU library."""
+    host_lib().rt_host_defer_jpeg_decode(bool(on))
+
+
+def read_texture(loaded: "LoadedScene", slot: int) -> np.ndarray:
+    """RGBA8 texels of texture `slot` as resident on the first device."""
+    w, h = _ffi.isize(), _ffi.isize()
+    gpu_check(gpu_lib().rt_gpu_read_texture(C.byref(loaded.scene), slot, None, C.byref(w), C.byref(h)))
+    out = np.zeros((h.value, w.value, 4), dtype=np.uint8)
+    gpu_check(gpu_lib().rt_gpu_read_texture(C.byref(loaded.scene), slot, out.ctypes.data, C.byref(w), C.byref(h)))
+    return out
+
+
 def look_at(eye, target, up=(0.0, 1.0, 0.0), fov_degrees: float = 70.0) -> Camera:
     cam = Camera()
     host_lib().rt_camera_look_at(C.byref(cam), Vec3(*eye), Vec3(*target), Vec3(*up),

@@ -18,6 +18,8 @@
  *   --split auto|samples|chunks   how (RT_GPU_Options.split_mode)      --reduce p2p|nccl   with what
  *   --dump-accum <file>    raw f32 W*H*3 sums of cast_ray (pre-division), little endian
  *   --dump-hit-ids <file>  raw i32 W*H primary-hit slots of sample 0 (-1 = miss)
+ *   --gpu-decode 1     JPEG textures stay compressed on the host and are decoded by nvJPEG during the scene upload
+ *                      (not byte-identical to the host decoder: INTEGRATION.md)
  *   --pinned 1         host buffers (texels, nodes, triangles, image) in pinned memory, DMA-read in place by every
  *                      upload (worth it for a host that re-uploads per frame; pinning ~60 MB costs more than
  *                      one staged upload, so a one-shot render keeps them pageable)
@@ -39,7 +41,7 @@ typedef struct {
   bool verbose, denoise, has_eye, has_target;
   f32 eye[3], target[3], fov_degrees;
   u32 seed;
-  int device, gpus, split_mode, reduce_mode, pinned;
+  int device, gpus, split_mode, reduce_mode, pinned, gpu_decode;
   char const *dump_accum, *dump_hit_ids;
 } Config;
 
@@ -70,6 +72,7 @@ static bool parse_args(int argc, char **argv, Config *c) {
       else if (!strcmp(arg, "--device")) c->device = atoi(val);
       else if (!strcmp(arg, "--gpus"))   c->gpus = atoi(val);
       else if (!strcmp(arg, "--pinned")) c->pinned = atoi(val);
+      else if (!strcmp(arg, "--gpu-decode")) c->gpu_decode = atoi(val);
       else if (!strcmp(arg, "--dump-accum"))   c->dump_accum = val;
       else if (!strcmp(arg, "--dump-hit-ids")) c->dump_hit_ids = val;
       else if (!strcmp(arg, "--split"))
@@ -119,6 +122,7 @@ int main(int argc, char **argv) {
   if (rt_gpu_init_devices(config.gpus, devices)) { fprintf(stderr, "%s\n", rt_gpu_last_error()); return 1; }
   f64 t_init_done = now_ms();
   if (config.pinned) rt_host_set_buffer_allocator(rt_gpu_host_alloc, rt_gpu_host_free);
+  if (config.gpu_decode) rt_host_defer_jpeg_decode(true);
 
   Image image = rt_image_alloc(config.width, config.height, 3);
 

@@ -314,9 +314,18 @@ static bool accessor_get(Gltf const *g, isize index, Accessor *a) {
   a->count = rt_json_int(rt_json_get(acc, "count"), 0);
   a->normalized = rt_json_num(rt_json_get(acc, "normalized"), 0) != 0;
   isize stride = rt_json_int(rt_json_get(bv, "byteStride"), 0);
-  a->stride = stride ? stride : a->n_comp * comp_size(a->comp_type);
-  size_t off = (size_t)rt_json_int(rt_json_get(bv, "byteOffset"), 0) + (size_t)rt_json_int(rt_json_get(acc, "byteOffset"), 0);
-  if (off + (size_t)(a->count ? (a->count - 1) * a->stride + a->n_comp * comp_size(a->comp_type) : 0) > g->buffer_len[buf]) return false;
+  isize elem = a->n_comp * comp_size(a->comp_type);
+  a->stride = stride ? stride : elem;
+  /* every number below comes from the file: reject negatives and check ranges without letting a sum wrap */
+  isize off_view = rt_json_int(rt_json_get(bv, "byteOffset"), 0), off_acc = rt_json_int(rt_json_get(acc, "byteOffset"), 0);
+  if (a->count < 0 || a->stride < elem || a->stride > (1 << 20) || off_view < 0 || off_acc < 0) return false;
+  size_t buflen = g->buffer_len[buf];
+  if ((size_t)off_view > buflen || (size_t)off_acc > buflen - (size_t)off_view) return false;
+  size_t off = (size_t)off_view + (size_t)off_acc, room = buflen - off;
+  if (a->count > 0) {
+    if ((size_t)elem > room) return false;
+    if ((size_t)(a->count - 1) > (room - (size_t)elem) / (size_t)a->stride) return false;
+  }
   a->base = g->buffers[buf] + off;
   return true;
 }
@@ -367,12 +376,19 @@ static void emit_mesh(Gltf const *g, RT_Json const *mesh, Mat4d xf, RT_Model *mo
     bool has_n = accessor_get(g, rt_json_int(rt_json_get(attrs, "NORMAL"), -1), &N);
     bool has_t = accessor_get(g, rt_json_int(rt_json_get(attrs, "TEXCOORD_0"), -1), &T);
     bool has_i = accessor_get(g, rt_json_int(rt_json_get(prim, "indices"), -1), &I);
-    if (!has_p) continue;
+    if (!has_p || P.n_comp < 3 || P.count < 1) continue;
+    if (has_n && N.n_comp < 3) has_n = false;
+    if (has_t && T.n_comp < 2) has_t = false;
     isize material = rt_json_int(rt_json_get(prim, "material"), -1);
     if (material < 0 || material >= model->n_materials - 1) material = model->n_materials - 1;
     isize n_idx = has_i ? I.count : P.count;
     for (isize k = 0; k + 2 < n_idx; k += 3) {
-      if (out->n == out->cap) { out->cap = out->cap ? out->cap * 2 : 4096; out->t = realloc(out->t, sizeof(Triangle) * (size_t)out->cap); }
+      if (out->n == out->cap) {
+        isize cap = out->cap ? out->cap * 2 : 4096;
+        Triangle *grown = realloc(out->t, sizeof(Triangle) * (size_t)cap);
+        if (!grown) { rt_host_set_error("gltf: out of memory"); return; }
+        out->t = grown; out->cap = cap;
+      }
       Triangle *t = &out->t[out->n++];
       memset(t, 0, sizeof *t);
       for (int j = 0; j < 3; j++) {
@@ -402,9 +418,10 @@ static bool load_gltf(char const *path, u8 *data, size_t len, Shader_Proc proc, 
   u8 const *bin = NULL; size_t bin_len = 0;
   if (len >= 20 && !memcmp(data, "glTF", 4)) {
     u32 clen; memcpy(&clen, data + 12, 4);
+    if ((size_t)clen > len - 20) { rt_host_set_error("glb: JSON chunk length exceeds the file"); return false; }
     json = (char const *)data + 20; json_len = clen;
     size_t off = 20 + (size_t)clen;
-    if (off + 8 <= len) { u32 blen; memcpy(&blen, data + off, 4); bin = data + off + 8; bin_len = blen; if (off + 8 + bin_len > len) bin_len = len - off - 8; }
+    if (off + 8 <= len) { u32 blen; memcpy(&blen, data + off, 4); bin = data + off + 8; bin_len = blen; if (bin_len > len - off - 8) bin_len = len - off - 8; }
   }
   RT_Json_Doc *doc = NULL;
   g.root = rt_json_parse(json, json_len, &doc);
@@ -416,6 +433,7 @@ static bool load_gltf(char const *path, u8 *data, size_t len, Shader_Proc proc, 
   g.buffers = calloc((size_t)g.n_buffers + 1, sizeof(u8 *));
   g.buffer_len = calloc((size_t)g.n_buffers + 1, sizeof(size_t));
   bool *owned = calloc((size_t)g.n_buffers + 1, sizeof(bool));
+  if (!g.buffers || !g.buffer_len || !owned) { rt_host_set_error("gltf: out of memory"); free(g.buffers); free(g.buffer_len); free(owned); rt_json_free(doc); return false; }
   for (isize i = 0; i < g.n_buffers; i++) {
     char const *uri = rt_json_str(rt_json_get(rt_json_at(bufs, i), "uri"));
     if (!uri) { g.buffers[i] = (u8 *)bin; g.buffer_len[i] = bin_len; continue; }
@@ -431,6 +449,12 @@ static bool load_gltf(char const *path, u8 *data, size_t len, Shader_Proc proc, 
   isize n_nodes = rt_json_len(nodes);
   Mat4d *global = malloc(sizeof(Mat4d) * (size_t)(n_nodes + 1));
   isize *parent = malloc(sizeof(isize) * (size_t)(n_nodes + 1));
+  if (!global || !parent) {
+    rt_host_set_error("gltf: out of memory");
+    for (isize i = 0; i < g.n_buffers; i++) if (owned[i]) free(g.buffers[i]);
+    free(owned); free(g.buffers); free(g.buffer_len); free(global); free(parent); rt_json_free(doc);
+    return false;
+  }
   for (isize i = 0; i < n_nodes; i++) parent[i] = -1;
   for (isize i = 0; i < n_nodes; i++) {
     RT_Json *kids = rt_json_get(rt_json_at(nodes, i), "children");
@@ -459,11 +483,13 @@ static bool load_gltf(char const *path, u8 *data, size_t len, Shader_Proc proc, 
   RT_Json *images = rt_json_get(g.root, "images");
   model->n_images = rt_json_len(images);
   model->images = calloc((size_t)model->n_images + 1, sizeof(Image));
+  if (!model->images) { rt_host_set_error("gltf: out of memory"); model->n_images = 0; }
   /* The reference decodes the images one after the other (stb_image, driver.c:620-626); decoding
    * four 2048x2048 JPEGs is the largest term of time-to-image once the render runs on GPUs, so each
    * image gets its own thread here.  Results do not depend on the schedule. */
   bool ok = true;
   Decode_Job *jobs = calloc((size_t)model->n_images + 1, sizeof(Decode_Job));
+  if (!jobs) { rt_host_set_error("gltf: out of memory"); model->n_images = 0; ok = false; }
   for (isize i = 0; i < model->n_images; i++) {
     RT_Json *im = rt_json_at(images, i);
     isize bv_index = rt_json_int(rt_json_get(im, "bufferView"), -1);
@@ -472,8 +498,9 @@ static bool load_gltf(char const *path, u8 *data, size_t len, Shader_Proc proc, 
     if (bv_index >= 0) {
       RT_Json *bv = rt_json_at(rt_json_get(g.root, "bufferViews"), bv_index);
       isize buf = rt_json_int(rt_json_get(bv, "buffer"), 0);
-      size_t off = (size_t)rt_json_int(rt_json_get(bv, "byteOffset"), 0), n = (size_t)rt_json_int(rt_json_get(bv, "byteLength"), 0);
-      if (buf < g.n_buffers && g.buffers[buf] && off + n <= g.buffer_len[buf]) { jobs[i].bytes = g.buffers[buf] + off; jobs[i].len = n; }
+      isize off = rt_json_int(rt_json_get(bv, "byteOffset"), 0), n = rt_json_int(rt_json_get(bv, "byteLength"), 0);
+      if (bv && buf >= 0 && buf < g.n_buffers && g.buffers[buf] && off >= 0 && n >= 0 && (size_t)off <= g.buffer_len[buf] &&
+          (size_t)n <= g.buffer_len[buf] - (size_t)off) { jobs[i].bytes = g.buffers[buf] + off; jobs[i].len = (size_t)n; }
       else snprintf(jobs[i].error, sizeof jobs[i].error, "bufferView %ld is out of range", (long)bv_index);
     } else if (uri && strncmp(uri, "data:", 5)) {
       jobs[i].path = sibling_path(path, uri);

@@ -34,6 +34,10 @@ void rt_camera_look_at(Camera *camera, Vec3 eye, Vec3 target, Vec3 up, f32 fov_r
 
 /* stb_image_load_bytes stand-in (driver.c:107,621): baseline JPEG and PNG. */
 bool rt_image_decode(u8 const *bytes, size_t len, Image *out);
+/* With deferral on, baseline JPEGs are not decoded on the host: rt_image_decode / rt_load_texture / the glTF loader
+ * return Images that carry the compressed bytes (pixel_type PT_RT_JPEG_BYTES, rt_base.h) for the GPU library to
+ * decode during the scene upload.  Such images cannot be sampled on the CPU. */
+void rt_host_defer_jpeg_decode(bool on);
 /* driver.c:106-116 */
 bool rt_load_texture(char const *path, Image *out);
 void rt_image_free(Image *image);

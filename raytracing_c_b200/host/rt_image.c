@@ -153,7 +153,47 @@ done:
   return ok;
 }
 
+/* With deferral on, a JPEG is NOT decoded here: the Image carries the compressed bytes (PT_RT_JPEG_BYTES) and the GPU
+ * library decodes them during the scene upload.  Size comes from the first SOF0/SOF1 marker. */
+static bool g_defer_jpeg = false;
+void rt_host_defer_jpeg_decode(bool on) { g_defer_jpeg = on; }
+
+static bool jpeg_frame_size(u8 const *p, size_t len, isize *w, isize *h, int *n_comp) {
+  size_t i = 2;
+  while (i + 4 <= len) {
+    if (p[i] != 0xff) return false;
+    u8 m = p[i + 1];
+    if (m == 0xff) { i++; continue; }
+    if (m == 0xd8 || (m >= 0xd0 && m <= 0xd7) || m == 0x01) { i += 2; continue; }
+    size_t seg = ((size_t)p[i + 2] << 8) | p[i + 3];
+    if (seg < 2 || i + 2 + seg > len) return false;
+    if (m == 0xc0 || m == 0xc1) {
+      if (seg < 8) return false;
+      *h = ((isize)p[i + 5] << 8) | p[i + 6];
+      *w = ((isize)p[i + 7] << 8) | p[i + 8];
+      *n_comp = p[i + 9];
+      return *w > 0 && *h > 0;
+    }
+    if (m == 0xc2 || m == 0xda) return false;        /* progressive, or a scan before any baseline frame */
+    i += 2 + seg;
+  }
+  return false;
+}
+
 bool rt_image_decode(u8 const *bytes, size_t len, Image *out) {
+  if (g_defer_jpeg && len >= 2 && bytes[0] == 0xff && bytes[1] == 0xd8) {
+    isize w = 0, h = 0; int nc = 0;
+    if (jpeg_frame_size(bytes, len, &w, &h, &nc) && (nc == 1 || nc == 3)) {
+      memset(out, 0, sizeof *out);
+      out->pixels.data = rt_host_buffer_alloc(len);
+      if (!out->pixels.data) { rt_host_set_error("out of memory"); return false; }
+      memcpy(out->pixels.data, bytes, len);
+      out->pixels.len = (isize)len;
+      out->width = w; out->height = h; out->stride = w;
+      out->components = 3; out->pixel_type = PT_RT_JPEG_BYTES;
+      return true;
+    }
+  }
   if (len >= 2 && bytes[0] == 0xff && bytes[1] == 0xd8) return rt_jpeg_decode(bytes, len, out);
   if (len >= 8 && bytes[0] == 0x89 && bytes[1] == 'P') return png_decode(bytes, len, out);
   rt_host_set_error("image: unknown format (baseline JPEG and PNG are supported)");

@@ -1,0 +1,64 @@
+"""Device-side texture decode: compressed JPEGs handed to the scene upload and decoded by nvJPEG,
+against the host decoder (host/rt_jpeg.c), which stays the parity path.  JPEG decoders may differ in IDCT rounding
+and chroma upsampling, so the bar here is closeness, measured and printed, not byte equality."""
+import ctypes as C
+import os
+import time
+
+import numpy as np
+import pytest
+
+from helpers import MODELS
+from raytracing_c_b200 import driver, gpu_lib
+from raytracing_c_b200._ffi import gpu_check
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _gpu():
+    gpu_check(gpu_lib().rt_gpu_init(0))
+    yield
+    driver.defer_jpeg_decode(False)
+    driver.set_options()
+
+
+def load_helmet(deferred):
+    driver.defer_jpeg_decode(deferred)
+    try:
+        t0 = time.perf_counter()
+        loaded = driver.load_scene(os.path.join(MODELS, "helmet.glb"))
+        return loaded, time.perf_counter() - t0
+    finally:
+        driver.defer_jpeg_decode(False)
+
+
+def test_nvjpeg_textures_are_close_to_the_host_decoder_and_render_the_same_picture():
+    gpu = gpu_lib()
+    host, t_host = load_helmet(False)
+    dev, t_dev = load_helmet(True)
+    try:
+        assert all(dev.model.images[i].pixel_type == 0x4A50 for i in range(dev.model.n_images)), "textures must stay compressed"
+        for loaded in (host, dev):
+            driver.register_callbacks(loaded)
+        t0 = time.perf_counter(); gpu_check(gpu.rt_gpu_scene_upload(C.byref(host.scene))); a0 = driver.read_texture(host, 0); t_up_host = time.perf_counter() - t0
+        t0 = time.perf_counter(); gpu_check(gpu.rt_gpu_scene_upload(C.byref(dev.scene))); b0 = driver.read_texture(dev, 0); t_up_dev = time.perf_counter() - t0
+        worst, equal = 0, []
+        for slot in range(int(host.model.n_images)):
+            a, b = driver.read_texture(host, slot), driver.read_texture(dev, slot)
+            assert a.shape == b.shape == (2048, 2048, 4)
+            diff = np.abs(a[..., :3].astype(int) - b[..., :3].astype(int))
+            worst = max(worst, int(diff.max()))
+            equal.append(float((diff == 0).mean()))
+            assert diff.mean() < 1.0, f"texture {slot}: mean abs difference {diff.mean()}"
+        w, h, spp = 480, 270, 64
+        pa = driver.render(host, w, h, spp, 8).astype(np.float64) / 255
+        pb = driver.render(dev, w, h, spp, 8).astype(np.float64) / 255
+        rmse = float(np.sqrt(np.mean((pa - pb) ** 2)))
+        print(f"\nnvJPEG vs host decoder: max abs texel diff {worst}, equal fraction per texture {['%.3f' % e for e in equal]}, "
+              f"render sRGB RMSE {rmse:.5f}; load+decode {1e3 * t_host:.0f} ms (host) vs {1e3 * t_dev:.0f} ms (deferred), "
+              f"first upload {1e3 * t_up_host:.0f} ms (texels over PCIe) vs {1e3 * t_up_dev:.0f} ms (nvJPEG on the device)")
+        assert worst <= 24 and rmse < 0.01
+    finally:
+        host.close()
+        dev.close()

@@ -105,3 +105,56 @@ def test_look_at_camera():
     m = np.array([[cam.view_matrix[r][c] for c in range(4)] for r in range(4)])
     assert np.allclose(m[:3, 3], [3, 0, 0]) and np.allclose(-m[:3, 2], [-1, 0, 0])     # looks down -Z of the camera
     assert np.allclose(m[:3, :3] @ m[:3, :3].T, np.eye(3), atol=1e-6)
+
+
+def _try_load(path):
+    """rt_load_model_file on a hostile file: must return (False or True) without touching memory it does not own."""
+    import ctypes as C
+    from raytracing_c_b200._ffi import Camera, Model, host_lib
+    host = host_lib()
+    model, cam = Model(), Camera()
+    ok = host.rt_load_model_file(str(path).encode(), None, C.byref(model), C.byref(cam))
+    if ok:
+        host.rt_model_free(C.byref(model))
+    return bool(ok)
+
+
+def test_malformed_glb_is_rejected_not_read_out_of_bounds(tmp_path):
+    """the GLB chunk length, accessor offsets/counts/strides and image bufferViews all come from the file."""
+    import json
+    import struct
+    good = open(os.path.join(MODELS, "spheres.glb"), "rb").read()
+    # (1) JSON chunk length larger than the file
+    bad = bytearray(good)
+    struct.pack_into("<I", bad, 12, len(good) * 4)
+    (tmp_path / "chunk.glb").write_bytes(bad)
+    assert not _try_load(tmp_path / "chunk.glb")
+    # (2) truncations at many lengths: never a crash, and a load that survives must free cleanly
+    for cut in (12, 19, 20, 21, 200, len(good) // 3, len(good) // 2, len(good) - 5):
+        (tmp_path / "cut.glb").write_bytes(good[:cut])
+        _try_load(tmp_path / "cut.glb")
+    # (3) hostile numbers in the JSON: negative offsets, counts, strides, buffer indices
+    clen = struct.unpack_from("<I", good, 12)[0]
+    doc = json.loads(good[20:20 + clen])
+    rest = good[20 + clen:]
+
+    def rebuild(d):
+        js = json.dumps(d).encode()
+        js += b" " * (-len(js) % 4)
+        body = struct.pack("<II", len(js), 0x4E4F534A) + js + rest
+        return b"glTF" + struct.pack("<II", 2, 12 + len(body)) + body
+
+    for mutate in (lambda d: d["accessors"][0].update(byteOffset=-4096),
+                   lambda d: d["accessors"][0].update(count=-7),
+                   lambda d: d["accessors"][0].update(count=2 ** 40),
+                   lambda d: d["bufferViews"][0].update(byteOffset=-1),
+                   lambda d: d["bufferViews"][0].update(byteOffset=2 ** 62),
+                   lambda d: d["bufferViews"][0].update(byteStride=-12),
+                   lambda d: d["bufferViews"][0].update(buffer=-3),
+                   lambda d: d["bufferViews"][0].update(buffer=99)):
+        d = json.loads(json.dumps(doc))
+        mutate(d)
+        (tmp_path / "hostile.glb").write_bytes(rebuild(d))
+        _try_load(tmp_path / "hostile.glb")          # may load (the primitive is skipped) or fail; must not crash
+    (tmp_path / "same.glb").write_bytes(rebuild(doc))
+    assert _try_load(tmp_path / "same.glb")
