@@ -129,6 +129,7 @@ HOST_EXPORTS = [
     "rt_image_decode", "rt_load_texture", "rt_image_free", "rt_image_alloc", "rt_generate_background",
     "rt_save_image", "rt_save_png", "rt_save_qoi", "rt_save_ppm", "rt_host_last_error",
     "rt_host_set_buffer_allocator", "rt_host_buffer_alloc", "rt_host_buffer_free", "rt_host_defer_jpeg_decode",
+    "scene_save_file", "scene_load_file",
 ]
 
 
@@ -173,6 +174,10 @@ def host_lib() -> C.CDLL:
         lib.rt_host_last_error.restype = C.c_char_p
         lib.rt_host_set_buffer_allocator.argtypes = [C.c_void_p, C.c_void_p]
         lib.rt_host_set_buffer_allocator.restype = None
+        lib.scene_save_file.restype = C.c_bool
+        lib.scene_save_file.argtypes = [C.c_char_p, C.POINTER(Scene), C.POINTER(PBRShaderData), isize]
+        lib.scene_load_file.restype = C.c_bool
+        lib.scene_load_file.argtypes = [C.c_char_p, C.POINTER(Scene), C.POINTER(PBRShaderData), isize, C.c_void_p]
         lib.rt_host_defer_jpeg_decode.argtypes = [C.c_bool]
         lib.rt_host_defer_jpeg_decode.restype = None
         _host = lib

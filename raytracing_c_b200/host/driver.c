@@ -18,6 +18,8 @@
  *   --split auto|samples|chunks   how (RT_GPU_Options.split_mode)      --reduce p2p|nccl   with what
  *   --dump-accum <file>    raw f32 W*H*3 sums of cast_ray (pre-division), little endian
  *   --dump-hit-ids <file>  raw i32 W*H primary-hit slots of sample 0 (-1 = miss)
+ *   --scene-cache <file>   load the BVH and triangle block from this file if it exists (and matches the model's
+ *                      triangle count), else build them and write it (reference scene.c:18-76; host/scene_cache.c)
  *   --gpu-decode 1     JPEG textures stay compressed on the host and are decoded by nvJPEG during the scene upload
  *                      (not byte-identical to the host decoder: INTEGRATION.md)
  *   --pinned 1         host buffers (texels, nodes, triangles, image) in pinned memory, DMA-read in place by every
@@ -42,7 +44,7 @@ typedef struct {
   f32 eye[3], target[3], fov_degrees;
   u32 seed;
   int device, gpus, split_mode, reduce_mode, pinned, gpu_decode;
-  char const *dump_accum, *dump_hit_ids;
+  char const *dump_accum, *dump_hit_ids, *scene_cache;
 } Config;
 
 static void print_usage(char const *argv0) {
@@ -73,6 +75,7 @@ static bool parse_args(int argc, char **argv, Config *c) {
       else if (!strcmp(arg, "--gpus"))   c->gpus = atoi(val);
       else if (!strcmp(arg, "--pinned")) c->pinned = atoi(val);
       else if (!strcmp(arg, "--gpu-decode")) c->gpu_decode = atoi(val);
+      else if (!strcmp(arg, "--scene-cache"))  c->scene_cache = val;
       else if (!strcmp(arg, "--dump-accum"))   c->dump_accum = val;
       else if (!strcmp(arg, "--dump-hit-ids")) c->dump_hit_ids = val;
       else if (!strcmp(arg, "--split"))
@@ -151,9 +154,20 @@ int main(int argc, char **argv) {
   }
 
   f64 t_bvh = now_ms();
-  scene_init(&scene, model.triangles);
+  bool cached = false;
+  if (config.scene_cache && access(config.scene_cache, R_OK) == 0) {
+    Camera keep = scene.camera;       /* the command line and the model decide the camera, not the cache */
+    cached = scene_load_file(config.scene_cache, &scene, model.materials, model.n_materials, rt_gpu_pbr_shader_proc);
+    scene.camera = keep;
+    if (!cached) fprintf(stderr, "scene cache '%s' not used: %s\n", config.scene_cache, rt_host_last_error());
+  }
+  if (!cached) {
+    scene_init(&scene, model.triangles);
+    if (config.scene_cache && !scene_save_file(config.scene_cache, &scene, model.materials, model.n_materials))
+      fprintf(stderr, "scene cache '%s' not written: %s\n", config.scene_cache, rt_host_last_error());
+  }
   if (config.verbose) {
-    printf("Bvh generated in %ldms\n", (long)(now_ms() - t_bvh));
+    printf("Bvh %s in %ldms\n", cached ? "loaded from the scene cache" : "generated", (long)(now_ms() - t_bvh));
     printf("Width:     %ld\nHeight:    %ld\nSamples:   %ld\nBounces:   %ld\nThreads:   %ld\n",
            (long)config.width, (long)config.height, (long)config.samples, (long)config.max_bounces, (long)config.n_threads);
     printf("BVH-Nodes: %ld\nBVH-Depth: %ld\nTriangles: %ld\n\n", (long)scene.bvh.nodes.len, (long)scene.bvh.depth, (long)model.triangles.len);

@@ -59,6 +59,12 @@ void  rt_host_set_buffer_allocator(void *(*alloc)(size_t), void (*release)(void 
 void *rt_host_buffer_alloc(size_t bytes);
 void  rt_host_buffer_free(void *p);
 
+/* The scene cache (reference scene.c:13-76, scene_save_writer / scene_load_bytes): the reference's container, with
+ * material indices where the reference writes raw Shader pointers (host/scene_cache.c).  A loaded scene owns its
+ * buffers like one from scene_init (scene_destroy releases them); `materials` / `proc` re-bind the shaders. */
+bool scene_save_file(char const *path, Scene const *scene, PBR_Shader_Data const *materials, isize n_materials);
+bool scene_load_file(char const *path, Scene *scene, PBR_Shader_Data *materials, isize n_materials, Shader_Proc proc);
+
 char const *rt_host_last_error(void);
 
 #ifdef __cplusplus

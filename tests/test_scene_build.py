@@ -1,6 +1,7 @@
 """scene_init (product host builder, raytracing_c_b200/host/scene_build.c) against the oracle's literal
 restatement of reference scene.c: byte-identical nodes, SoA positions and AoS records."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -73,3 +74,43 @@ def test_degenerate_uvs_and_zero_area():
     tris[:, 2, 1] = np.arange(12) % 2          # every other triangle has zero area -> NaN normal, same on both sides
     a, b, *_ = build_both(tris)
     assert a == b
+
+
+def test_scene_cache_round_trip_and_rejections(tmp_path):
+    """Scene cache (reference scene.c:18-76, host/scene_cache.c): same container, material indices instead of the
+    reference's raw pointers.  A loaded scene has the same bytes, re-bound shaders, and renders the same radiance."""
+    import ctypes as C
+    import struct
+    from raytracing_c_b200._ffi import Scene, host_lib
+    from helpers import scene_buffers
+    host = host_lib()
+    loaded = load("helmet.glb")
+    try:
+        path = str(tmp_path / "helmet.scene")
+        assert host.scene_save_file(path.encode(), C.byref(loaded.scene), loaded.model.materials, loaded.model.n_materials)
+        n_nodes, n_slots = loaded.scene.bvh.nodes.len, loaded.scene.triangles.len
+        assert os.path.getsize(path) == 96 + n_nodes * 192 + n_slots * (36 + 112)         # header aligned to 32 B (scene.c:13-16)
+        back = Scene()
+        assert host.scene_load_file(path.encode(), C.byref(back), loaded.model.materials, loaded.model.n_materials, loaded.shader_proc)
+        assert scene_buffers(back) == scene_buffers(loaded.scene)
+        aos_a = np.frombuffer(C.string_at(loaded.scene.triangles.aos, n_slots * 112), dtype=np.uint64).reshape(n_slots, 14)
+        aos_b = np.frombuffer(C.string_at(back.triangles.aos, n_slots * 112), dtype=np.uint64).reshape(n_slots, 14)
+        assert np.array_equal(aos_a[:, 12:], aos_b[:, 12:]), "Shader {data, proc} pointers must be re-bound identically"
+        back.background = loaded.scene.background
+        want = oracle_ffi.render(loaded, 48, 32, 2, n_threads=2)["accum"]
+        keep = loaded.scene
+        loaded.scene = back
+        got = oracle_ffi.render(loaded, 48, 32, 2, n_threads=2)["accum"]
+        loaded.scene = keep
+        assert np.array_equal(got, want)
+        host.scene_destroy(C.byref(back))
+        # rejections: truncated, padded, version 0 (the reference's raw-pointer files), hostile counts
+        data = open(path, "rb").read()
+        for name, blob in (("cut", data[:-7]), ("pad", data + b"\0" * 32), ("v0", struct.pack("<i", 0) + data[4:]),
+                           ("nodes", data[:4] + struct.pack("<i", 2 ** 30) + data[8:])):
+            p = str(tmp_path / f"{name}.scene")
+            open(p, "wb").write(blob)
+            assert not host.scene_load_file(p.encode(), C.byref(Scene()), loaded.model.materials, loaded.model.n_materials, loaded.shader_proc), name
+        assert b"version 0" in host.rt_host_last_error() or b"disagree" in host.rt_host_last_error()
+    finally:
+        loaded.close()
