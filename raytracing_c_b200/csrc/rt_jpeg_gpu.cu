@@ -15,6 +15,7 @@
 #include <nvjpeg.h>      // types only
 
 #include <mutex>
+#include <vector>
 
 #include "rt_state.h"
 
@@ -30,7 +31,10 @@ struct NvJpeg {
   nvjpegStatus_t (*GetImageInfo)(nvjpegHandle_t, const unsigned char *, size_t, int *, nvjpegChromaSubsampling_t *, int *, int *) = nullptr;
   nvjpegStatus_t (*Decode)(nvjpegHandle_t, nvjpegJpegState_t, const unsigned char *, size_t, nvjpegOutputFormat_t, nvjpegImage_t *, cudaStream_t) = nullptr;
   nvjpegHandle_t handle = nullptr;
-  nvjpegJpegState_t state = nullptr;
+  // one decoder state per image in flight: a state's pinned staging is still being read by the stream after
+  // nvjpegDecode returns, so it is not reused before jpeg_begin_batch has drained that stream
+  std::vector<nvjpegJpegState_t> states;
+  size_t next_state = 0;
 } nj;
 
 int nvjpeg_load() {
@@ -52,10 +56,16 @@ int nvjpeg_load() {
       return fail("device JPEG decode: libnvjpeg lacks an expected symbol");
   }
   if (nj.CreateSimple(&nj.handle) != NVJPEG_STATUS_SUCCESS) { nj.handle = nullptr; return fail("nvjpegCreateSimple failed"); }
-  if (nj.StateCreate(nj.handle, &nj.state) != NVJPEG_STATUS_SUCCESS) return fail("nvjpegJpegStateCreate failed");
   return 0;
 }
 }  // namespace
+
+// Call once before the decodes of one upload: waits for the decodes of the previous one, then hands out states from the start.
+int jpeg_begin_batch(cudaStream_t stream) {
+  if (nj.next_state) CUDA_TRY(cudaStreamSynchronize(stream));
+  nj.next_state = 0;
+  return 0;
+}
 
 // Decodes `bytes` into interleaved RGB8 at d_rgb (pitch 3 * width) on `stream`; width/height must match the header.
 int jpeg_decode_device(const unsigned char *bytes, size_t len, int width, int height, unsigned char *d_rgb, cudaStream_t stream) {
@@ -68,15 +78,21 @@ int jpeg_decode_device(const unsigned char *bytes, size_t len, int width, int he
   nvjpegImage_t out{};
   out.channel[0] = d_rgb;
   out.pitch[0] = (size_t)width * 3;
-  nvjpegStatus_t st = nj.Decode(nj.handle, nj.state, bytes, len, NVJPEG_OUTPUT_RGBI, &out, stream);
+  if (nj.next_state == nj.states.size()) {
+    nvjpegJpegState_t st = nullptr;
+    if (nj.StateCreate(nj.handle, &st) != NVJPEG_STATUS_SUCCESS) return fail("nvjpegJpegStateCreate failed");
+    nj.states.push_back(st);
+  }
+  nvjpegStatus_t st = nj.Decode(nj.handle, nj.states[nj.next_state++], bytes, len, NVJPEG_OUTPUT_RGBI, &out, stream);
   if (st != NVJPEG_STATUS_SUCCESS) return fail("device JPEG decode: nvjpegDecode failed (%d)", (int)st);
   return 0;
 }
 
 void jpeg_shutdown() {
-  if (nj.state) nj.StateDestroy(nj.state);
+  for (nvjpegJpegState_t st : nj.states) nj.StateDestroy(st);
+  nj.states.clear();
+  nj.next_state = 0;
   if (nj.handle) nj.Destroy(nj.handle);
-  nj.state = nullptr;
   nj.handle = nullptr;
 }
 

@@ -373,6 +373,9 @@ static int upload_primary(Device &d, const HostScene &hs, const ArenaLayout &L, 
     CUDA_TRY(cudaStreamSynchronize(d.copy));
     if (grow(&d.d_texel_stage, &d.texel_stage_bytes, raw_max)) return 1;
   }
+  bool any_jpeg = false;
+  for (const Image *im : hs.images) any_jpeg |= im->pixel_type == PT_RT_JPEG_BYTES;
+  if (any_jpeg && jpeg_begin_batch(d.copy)) return 1;
   std::vector<size_t> order;
   if (hs.env_slot >= 0) order.push_back((size_t)hs.env_slot);
   for (size_t i = 0; i < hs.images.size(); i++) if ((int)i != hs.env_slot) order.push_back(i);

@@ -117,6 +117,7 @@ void release_device(Device &d);                               // everything the 
 void set_l2_window(Device &d, const DeviceScene &ds, cudaStream_t stream);
 
 // ---- rt_jpeg_gpu.cu
+int jpeg_begin_batch(cudaStream_t stream);
 int jpeg_decode_device(const unsigned char *bytes, size_t len, int width, int height, unsigned char *d_rgb, cudaStream_t stream);
 void jpeg_shutdown();
 
