@@ -437,15 +437,15 @@ static int upload_peer(Device &d, const Device &src_dev, const DeviceScene &src,
 // streams around it.
 void set_l2_window(Device &d, const DeviceScene &ds, cudaStream_t stream) {
   if (!ds.hot_base || !ds.hot_bytes) return;
-  static int disabled = -1;
-  if (disabled < 0) { const char *e = getenv("RT_GPU_NO_L2_WINDOW"); disabled = (e && e[0] == '1') ? 1 : 0; }
-  if (disabled) return;
+  // measured (profiles/r02_summary.md): no effect with the 13 MB head, -7 % with the whole arena — the kernels that read
+  // the scene are issue-bound, not waiting for evicted lines.  Off unless RT_GPU_L2_WINDOW=hot|all asks for it.
+  static int mode = -1;
+  if (mode < 0) { const char *e = getenv("RT_GPU_L2_WINDOW"); mode = !e ? 0 : !strcmp(e, "all") ? 2 : !strcmp(e, "hot") ? 1 : 0; }
+  if (mode == 0) return;
   if (!d.l2_persist_max || !d.l2_window_max) return;
   if (d.l2_stream == stream && d.l2_base == ds.hot_base) return;
   size_t want = ds.hot_bytes;
-  static int whole = -1;          // experiment knob: the whole arena (all texels) instead of its head
-  if (whole < 0) { const char *e = getenv("RT_GPU_L2_WINDOW"); whole = (e && !strcmp(e, "all")) ? 1 : 0; }
-  if (whole && !ds.blocks.empty()) want = ds.blocks[0].bytes;
+  if (mode == 2 && !ds.blocks.empty()) want = ds.blocks[0].bytes;        // the whole arena (all texels) instead of its head
   if (want > d.l2_window_max) want = d.l2_window_max;
   const size_t carve = want < d.l2_persist_max ? want : d.l2_persist_max;
   if (!d.l2_window_set) { cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve); d.l2_window_set = true; }
