@@ -85,6 +85,10 @@ typedef struct {
   i32   reduce_mode;      /* N devices: RT_GPU_REDUCE_* */
   i32   pixel_rank;       /* multi-PROCESS hosts: this process renders the 32x32 chunks congruent to */
   i32   pixel_world;      /* pixel_rank modulo pixel_world (<= 1: the whole image) */
+  i32   fast_math;        /* 0 (default): every sample bit-identical to the reference arithmetic.  1: the bounce
+                           * stages (trace of bounce >= 1, environment, BSDF) run FMA-contracted with hardware
+                           * transcendentals (csrc/rt_render_fast.cu); primary-hit ids, ray generation and the film
+                           * stay exact.  Faster, statistically equivalent, NOT bit-identical. */
 } RT_GPU_Options;
 void rt_gpu_set_options(RT_GPU_Options const *options);
 void rt_gpu_get_options(RT_GPU_Options *options);

@@ -94,7 +94,7 @@ class GPUOptions(C.Structure):
     _fields_ = [("user_seed", C.c_uint32), ("sample_begin", C.c_int32), ("sample_end", C.c_int32),
                 ("slice_samples", C.c_int32), ("keep_hit_ids", C.c_int32), ("sample_range_set", C.c_int32),
                 ("split_mode", C.c_int32), ("reduce_mode", C.c_int32), ("pixel_rank", C.c_int32),
-                ("pixel_world", C.c_int32)]
+                ("pixel_world", C.c_int32), ("fast_math", C.c_int32)]
 
 
 SPLIT_AUTO, SPLIT_SAMPLES, SPLIT_CHUNKS = 0, 1, 2

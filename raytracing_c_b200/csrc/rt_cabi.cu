@@ -167,6 +167,7 @@ int render_on_device(Device &d, const Scene *scene, isize width, isize height, c
   if (d.busy_valid) CUDA_TRY(cudaStreamWaitEvent(stream, d.busy, 0));
   CUDA_TRY(cudaStreamWaitEvent(stream, ds.geom_ready, 0));
   p.shading_ready = ds.tex_ready;
+  p.fast = g.options.fast_math != 0;
   set_l2_window(d, ds, stream);
   p.width = (int)width; p.height = (int)height;
   p.split_rank = share.split_rank; p.split_world = share.split_world;

@@ -66,6 +66,7 @@ struct ReduceParts { const float *part[RT_MAX_PARTS]; int n; };
 struct RenderParams {
   SceneDev  scene;
   int       width, height;
+  int       fast;                        // bounce stages from rt_render_fast.cu (RT_GPU_Options.fast_math)
   int       split_rank, split_world;     // pixel-space split over 32x32 chunks (rt_render.cu), world <= 1 = whole image
   cudaEvent_t shading_ready;             // optional: textures/environment complete (the primary trace does not wait for it)
   int       sample_begin, sample_end, max_bounces;

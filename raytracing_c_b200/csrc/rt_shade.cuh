@@ -14,6 +14,26 @@
 
 #include "rt_device.cuh"
 
+// Exact build (default): rt_math.h transcendentals and the reference's f64 promotions, bit-identical to the CPU oracle.
+// RT_FAST build (rt_render_fast.cu, opt-in): hardware approximations (MUFU lg2/ex2/sin/cos), CUDA's f32 atan2/asin,
+// f32 everywhere — a few ulp off per call, and one flipped lobe pick sends a path elsewhere, so the results are
+// compared with the oracle statistically (bench.py --fast: parity key), not bit for bit.
+#if defined(RT_FAST) && RT_FAST
+typedef float rt_real;
+#define RT_PI_R 3.14159265358979323846f
+__device__ __forceinline__ float m_pow_positive(float x, float y) { return __powf(x, y); }
+__device__ __forceinline__ float m_atan2(float y, float x) { return atan2f(y, x); }
+__device__ __forceinline__ float m_asin(float x) { return asinf(x); }
+__device__ __forceinline__ void  m_sincos(float a, float *s, float *c) { __sincosf(a, s, c); }
+#else
+typedef double rt_real;
+#define RT_PI_R RT_PI
+__device__ __forceinline__ float m_pow_positive(float x, float y) { return rt_powf_positive(x, y); }
+__device__ __forceinline__ float m_atan2(float y, float x) { return rt_atan2f(y, x); }
+__device__ __forceinline__ float m_asin(float x) { return rt_asinf(x); }
+__device__ __forceinline__ void  m_sincos(float a, float *s, float *c) { rt_sincosf(a, s, c); }
+#endif
+
 struct ShadeIn  { V3 dir, normal, normal_geo, tangent, bitangent; float u, v; };
 struct ShadeOut { V3 dir, tint, emission; bool terminate; };
 
@@ -26,7 +46,7 @@ __device__ __forceinline__ V3 texel_rgb(const TextureDev &tex, const float *lut,
 }
 
 // driver.c:49-93: negative wrap, fract, no half-texel offset, +1 neighbour clamped
-__device__ __noinline__ V3 sample_bilinear(const TextureDev &tex, const float *lut, float u, float v) {
+static __device__ __noinline__ V3 sample_bilinear(const TextureDev &tex, const float *lut, float u, float v) {
   if (u < 0) u += (float)(-(int)u + 1);
   if (v < 0) v += (float)(-(int)v + 1);
   u = u - floorf(u);
@@ -45,17 +65,17 @@ __device__ __noinline__ V3 sample_bilinear(const TextureDev &tex, const float *l
 // common.h:82-88.  The argument of the power is >= 0.055 / 1.055 (texel values are >= 0), so the
 // case analysis of rt_powf can be skipped: rt_powf_positive is bit-identical there.
 __device__ __forceinline__ V3 decode_srgb(V3 c) {
-  return mk3(rt_powf_positive((c.x + 0.055f) / 1.055f, 2.4f),
-             rt_powf_positive((c.y + 0.055f) / 1.055f, 2.4f),
-             rt_powf_positive((c.z + 0.055f) / 1.055f, 2.4f));
+  return mk3(m_pow_positive((c.x + 0.055f) / 1.055f, 2.4f),
+             m_pow_positive((c.y + 0.055f) / 1.055f, 2.4f),
+             m_pow_positive((c.z + 0.055f) / 1.055f, 2.4f));
 }
 
 // driver.c:95-104 (asin argument clamped: DESIGN.md deviation list)
-__device__ __noinline__ V3 environment(const SceneDev &sc, const float *lut, V3 dir) {
-  float inv_pi     = (float)(1.0f / RT_PI);
-  float inv_two_pi = (float)(1.0f / (2.0f * RT_PI));
-  float u = 0.5f + rt_atan2f(dir.z, dir.x) * inv_two_pi;
-  float v = 0.5f - rt_asinf(clamp1(dir.y, -1.0f, 1.0f)) * inv_pi;
+static __device__ __noinline__ V3 environment(const SceneDev &sc, const float *lut, V3 dir) {
+  float inv_pi     = (float)(1.0f / RT_PI_R);
+  float inv_two_pi = (float)(1.0f / (2.0f * RT_PI_R));
+  float u = 0.5f + m_atan2(dir.z, dir.x) * inv_two_pi;
+  float v = 0.5f - m_asin(clamp1(dir.y, -1.0f, 1.0f)) * inv_pi;
   return decode_srgb(sample_bilinear(sc.textures[sc.env_texture], lut, u, v));
 }
 
@@ -69,23 +89,23 @@ __device__ __forceinline__ float schlick1(float f0, float f90, float c) { return
 __device__ __forceinline__ float ggx_d(float roughness, float n_h) {       // k = 2 at both call sites
   float a2 = roughness * roughness;
   float b  = (n_h * n_h) * (a2 * a2 - 1) + 1;
-  return (float)(a2 / (RT_PI * (b * b)));
+  return (float)(a2 / (RT_PI_R * (b * b)));
 }
 
 // driver.c:217-221
 __device__ __forceinline__ float smith_g1(float n_v, float alpha2) {
   float a = alpha2 * alpha2;
   float b = n_v * n_v;
-  return (float)((2.0 * n_v) / (n_v + __fsqrt_rn(a + b - a * b)));
+  return (float)(((rt_real)2.0 * n_v) / (n_v + __fsqrt_rn(a + b - a * b)));
 }
 
 // driver.c:118-127
 __device__ __forceinline__ V3 cosine_hemisphere(uint32_t &rng) {
-  float angle  = (float)(rnd(rng) * 2 * RT_PI);
+  float angle  = (float)(rnd(rng) * 2 * RT_PI_R);
   float radius = __fsqrt_rn(rnd(rng));
   V3 d;
   float sn, cs;
-  rt_sincosf(angle, &sn, &cs);
+  m_sincos(angle, &sn, &cs);
   d.x = sn * radius;
   d.y = cs * radius;
   d.z = __fsqrt_rn(1 - radius * radius);
@@ -100,16 +120,16 @@ __device__ __forceinline__ V3 sample_vndf(V3 V, float ax, float ay, uint32_t &rn
   V3 T2 = cross3(Vh, T1);
 
   float r   = __fsqrt_rn(rnd(rng));
-  float phi = (float)(2.0 * RT_PI * rnd(rng));
+  float phi = (float)((rt_real)2.0 * RT_PI_R * rnd(rng));
   float sn, cs;
-  rt_sincosf(phi, &sn, &cs);
+  m_sincos(phi, &sn, &cs);
   float t1  = r * cs;
   float t2  = r * sn;
-  float s   = (float)(0.5 * (1.0 + Vh.z));
-  t2        = (float)((1.0 - s) * __fsqrt_rn((float)(1.0 - t1 * t1)) + s * t2);
+  float s   = (float)((rt_real)0.5 * ((rt_real)1.0 + Vh.z));
+  t2        = (float)(((rt_real)1.0 - s) * __fsqrt_rn((float)((rt_real)1.0 - t1 * t1)) + s * t2);
 
-  double rem = 1.0 - t1 * t1 - t2 * t2;
-  float  h   = __fsqrt_rn((float)(0.0 > rem ? 0.0 : rem));
+  rt_real rem = (rt_real)1.0 - t1 * t1 - t2 * t2;
+  float   h   = __fsqrt_rn((float)((rt_real)0.0 > rem ? (rt_real)0.0 : rem));
   V3 Nh = add3(add3(scale3(T1, t1), scale3(T2, t2)), scale3(Vh, h));
   return normalize3(mk3(ax * Nh.x, ay * Nh.y, (0.0 > Nh.z ? 0.0f : Nh.z)));
 }
@@ -125,7 +145,7 @@ __device__ __forceinline__ V3 sheen_term(float sheen, V3 base, float sheen_tint,
 }
 
 // driver.c:350-409 with :287-348 inlined
-__device__ __noinline__ void shade_pbr(const SceneDev &sc, const float *lut, int material, const ShadeIn &in, uint32_t &rng, ShadeOut &out) {
+static __device__ __noinline__ void shade_pbr(const SceneDev &sc, const float *lut, int material, const ShadeIn &in, uint32_t &rng, ShadeOut &out) {
   const MaterialDev &mat = sc.materials[material];
 
   // driver.c:129-153
@@ -194,11 +214,11 @@ __device__ __noinline__ void shade_pbr(const SceneDev &sc, const float *lut, int
     float n_l = wo.z, n_v = wi.z;
     if (!(n_l <= 0 || n_v <= 0)) {
       float l_h = dot3(wo, h);
-      float pdf = (float)(n_l / RT_PI);
+      float pdf = (float)(n_l / RT_PI_R);
       float fd90 = 0.5f + 2 * roughness * l_h * l_h;
       float fa = schlick1(1.0f, fd90, n_l);
       float fb = schlick1(1.0f, fd90, n_v);
-      V3 diff = scale3(base, (float)(fa * fb / RT_PI));
+      V3 diff = scale3(base, (float)(fa * fb / RT_PI_R));
       diff = mul3(diff, sub3(mk3(1, 1, 1), F));
       diff = add3(diff, sheen_term(mat.sheen, base, mat.sheen_tint, l_h));
       fx = diff.x * n_l; fy = diff.y * n_l; fz = diff.z * n_l;

@@ -44,6 +44,15 @@ __device__ __forceinline__ float child_entry_any(float lox, float loy, float loz
 template <bool REL>
 __device__ __forceinline__ float child_entry_regular(float nx, float ny, float nz, float fx, float fy, float fz,
                                                      float ox, float oy, float oz, float ix, float iy, float iz, float t_max) {
+#if defined(RT_FAST) && RT_FAST
+  // fast build: (plane - o) * i as one fused multiply-add, plane * i + (-o * i); the caller hands in -o * i for o
+  // (12 instead of 18 instructions per box; not the reference's rounding)
+  if (!REL) {
+    float enter = fmaxf(fmaxf(fmaf(nx, ix, ox), fmaf(ny, iy, oy)), fmaxf(fmaf(nz, iz, oz), RT_EPS));
+    float leave = fminf(fminf(fmaf(fx, ix, ox), fmaf(fy, iy, oy)), fminf(fmaf(fz, iz, oz), t_max));
+    return (enter >= leave) ? CUDART_INF_F : enter;
+  }
+#endif
   if (!REL) { nx -= ox; ny -= oy; nz -= oz; fx -= ox; fy -= oy; fz -= oz; }
   float enter = fmaxf(fmaxf(nx * ix, ny * iy), fmaxf(nz * iz, RT_EPS));
   float leave = fminf(fminf(fx * ix, fy * iy), fminf(fz * iz, t_max));
@@ -73,7 +82,7 @@ __device__ __forceinline__ void node_entries_regular(const float4 *__restrict__ 
 
 // out of line and by value: the rare path must not cost the common one registers or code
 struct Entries8 { float4 lo, hi; };
-__device__ __noinline__ Entries8 node_entries_any(const float4 *__restrict__ n4, float ox, float oy, float oz,
+static __device__ __noinline__ Entries8 node_entries_any(const float4 *__restrict__ n4, float ox, float oy, float oz,
                                                   float ix, float iy, float iz, float t_max) {
   Entries8 r;
   {
@@ -147,7 +156,11 @@ __device__ __forceinline__ bool walk_misses_root(const RayWalk &w, const SceneDe
   const float ny = (w.near_rows & 2u) ? sc.root_hi[1] : sc.root_lo[1], fy = (w.near_rows & 2u) ? sc.root_lo[1] : sc.root_hi[1];
   const float nz = (w.near_rows & 4u) ? sc.root_hi[2] : sc.root_lo[2], fz = (w.near_rows & 4u) ? sc.root_lo[2] : sc.root_hi[2];
   // (the root box itself is not stored relative: six subtractions per ray, once)
+#if defined(RT_FAST) && RT_FAST
+  return child_entry_regular<false>(nx, ny, nz, fx, fy, fz, -w.ox * w.ix, -w.oy * w.iy, -w.oz * w.iz, w.ix, w.iy, w.iz, CUDART_INF_F) == CUDART_INF_F;
+#else
   return child_entry_regular<false>(nx, ny, nz, fx, fy, fz, w.ox, w.oy, w.oz, w.ix, w.iy, w.iz, CUDART_INF_F) == CUDART_INF_F;
+#endif
 }
 
 // One node step: (box-test the node just entered,) pick the next child; ends with a leaf to test,
@@ -160,7 +173,11 @@ __device__ __forceinline__ void walk_node_step(RayWalk &w, const SceneDev &sc, f
       const float4 *n4 = (const float4 *)(sc.nodes + (size_t)w.node * 48);
       if (w.regular) {
         if (REL) node_entries_regular<true >((const float4 *)(sc.nodes_rel + (size_t)w.node * 48), w.near_rows, 0, 0, 0, w.ix, w.iy, w.iz, w.hit_t, e);
+#if defined(RT_FAST) && RT_FAST
+        else     node_entries_regular<false>(n4, w.near_rows, -w.ox * w.ix, -w.oy * w.iy, -w.oz * w.iz, w.ix, w.iy, w.iz, w.hit_t, e);
+#else
         else     node_entries_regular<false>(n4, w.near_rows, w.ox, w.oy, w.oz, w.ix, w.iy, w.iz, w.hit_t, e);
+#endif
       } else {
         const Entries8 r = node_entries_any(n4, w.ox, w.oy, w.oz, w.ix, w.iy, w.iz, w.hit_t);
         e[0] = r.lo.x; e[1] = r.lo.y; e[2] = r.lo.z; e[3] = r.lo.w; e[4] = r.hi.x; e[5] = r.hi.y; e[6] = r.hi.z; e[7] = r.hi.w;

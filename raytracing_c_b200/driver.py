@@ -147,9 +147,9 @@ def image_view(pixels: np.ndarray) -> Image:
 
 def set_options(user_seed: int = 0, sample_begin: int = 0, sample_end: int = 0, slice_samples: int = 0,
                 keep_hit_ids: bool = False, sample_range_set: bool = False, split_mode: int = 0, reduce_mode: int = 0,
-                pixel_rank: int = 0, pixel_world: int = 0) -> None:
+                pixel_rank: int = 0, pixel_world: int = 0, fast_math: bool = False) -> None:
     opt = GPUOptions(user_seed, sample_begin, sample_end, slice_samples, int(keep_hit_ids), int(sample_range_set),
-                     split_mode, reduce_mode, pixel_rank, pixel_world)
+                     split_mode, reduce_mode, pixel_rank, pixel_world, int(fast_math))
     gpu_lib().rt_gpu_set_options(C.byref(opt))
 
 

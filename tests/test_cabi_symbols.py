@@ -40,7 +40,7 @@ def test_host_library_exports_every_declared_entry_point():
 
 def test_struct_layouts_match_the_headers():
     assert C.sizeof(_ffi.Triangle) == 112 and C.sizeof(_ffi.Scene) == 208 and C.sizeof(_ffi.RenderingContext) == 80
-    assert C.sizeof(_ffi.Image) == 48 and C.sizeof(_ffi.PBRShaderData) == 80 and C.sizeof(_ffi.GPUOptions) == 40
+    assert C.sizeof(_ffi.Image) == 48 and C.sizeof(_ffi.PBRShaderData) == 80 and C.sizeof(_ffi.GPUOptions) == 44
 
 
 def test_no_gpu_means_a_loud_error_not_a_fallback():
