@@ -42,6 +42,10 @@ int         rt_gpu_sm_count(void);
  * the roofline denominator for the trace kernel (csrc/rt_peak.cu). */
 f64         rt_gpu_measure_fp32_issue(void);
 
+/* Optional: allocate what a frame of this size needs (accumulators, path-queue workspace on every device) now, e.g.
+ * on the thread that created the contexts while the model is still loading. */
+int         rt_gpu_prepare_frame(isize width, isize height, isize samples, isize max_bounces);
+
 /* ---- callbacks the device code internalises ----
  * Replaces the per-triangle Shader.proc indirect call (reference scene.h:30-35,
  * raytracer.c:535) and Scene.background.proc (scene.h:65-70, raytracer.c:554).

@@ -111,7 +111,7 @@ GPU_EXPORTS = [
     # rt_gpu.h
     "rt_gpu_init", "rt_gpu_init_devices", "rt_gpu_device_count", "rt_gpu_visible_devices", "rt_gpu_shutdown",
     "rt_gpu_last_error", "rt_gpu_last_status", "rt_gpu_sm_count", "rt_gpu_measure_fp32_issue",
-    "rt_gpu_host_alloc", "rt_gpu_host_free", "rt_gpu_last_frame_breakdown",
+    "rt_gpu_host_alloc", "rt_gpu_host_free", "rt_gpu_prepare_frame", "rt_gpu_last_frame_breakdown",
     "rt_gpu_shard_samples", "rt_gpu_shard_mode", "rt_gpu_shard_chunks",
     "rt_gpu_render_shard_device", "rt_gpu_accum_buffer", "rt_gpu_ipc_export", "rt_gpu_ipc_open",
     "rt_gpu_reduce_resolve_device", "rt_gpu_lightmap_bake",
@@ -192,6 +192,7 @@ def gpu_lib() -> C.CDLL:
         lib = C.CDLL(GPU_LIB)
         lib.rt_gpu_init.argtypes = [C.c_int]
         lib.rt_gpu_init_devices.argtypes = [C.c_int, C.POINTER(C.c_int)]
+        lib.rt_gpu_prepare_frame.argtypes = [isize, isize, isize, isize]
         lib.rt_gpu_host_alloc.restype = C.c_void_p
         lib.rt_gpu_host_alloc.argtypes = [C.c_size_t]
         lib.rt_gpu_host_free.argtypes = [C.c_void_p]

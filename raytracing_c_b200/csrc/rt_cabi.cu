@@ -129,7 +129,7 @@ int ensure_workspace(Device &d, size_t want, size_t floor_bytes, cudaStream_t st
   if (d.workspace_denied && want >= d.workspace_denied && d.workspace_bytes >= floor_bytes) return 0;
   CUDA_TRY(cudaStreamSynchronize(stream));      // an earlier launch may still read the old queues
   CUDA_TRY(cudaStreamSynchronize(d.stream));
-  size_t ask = want;
+  size_t ask = want + want / 50;      // 2 % headroom: a slightly larger request later (another split, another slice) fits
   for (;;) {
     if (d.d_workspace) { cudaFree(d.d_workspace); d.d_workspace = nullptr; d.workspace_bytes = 0; }
     if (cudaMalloc(&d.d_workspace, ask) == cudaSuccess) { d.workspace_bytes = ask; break; }
@@ -317,6 +317,31 @@ void *rt_gpu_host_alloc(size_t bytes) {
 
 void rt_gpu_host_free(void *p) {
   if (p) cudaFreeHost(p);
+}
+
+// Allocates what a frame of this size will need (accumulators, image, path-queue workspace on every device) ahead of
+// the first render, so the allocations (tens of ms for a 34 GB workspace) can overlap the host's model load.
+int rt_gpu_prepare_frame(isize width, isize height, isize samples, isize max_bounces) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  if (ensure_init()) return 1;
+  if (width < 1 || height < 1 || samples < 1 || max_bounces < 1) return fail("prepare_frame: empty frame");
+  const size_t n_dev = g.devs.size();
+  if (n_dev > 1 && enable_peers()) return 1;
+  const i32 mode = n_dev > 1 ? rt_gpu_shard_mode((i32)samples, (i32)n_dev, g.options.split_mode) : RT_GPU_SPLIT_SAMPLES;
+  const int world = n_dev > 1 && mode == RT_GPU_SPLIT_CHUNKS ? (int)n_dev : 1;
+  isize share = samples;
+  if (n_dev > 1 && mode == RT_GPU_SPLIT_SAMPLES) share = (samples + (isize)n_dev - 1) / (isize)n_dev;
+  isize slice = g.options.slice_samples > 0 ? g.options.slice_samples : rt_render_chunk_samples((int)width, (int)height, world);
+  if (slice > share) slice = share;
+  for (Device &d : g.devs) {
+    if (ensure_frame_buffers(d, (size_t)width * (size_t)height, g.options.keep_hit_ids != 0)) return 1;
+    const size_t want = rt_render_workspace_bytes((int)width, (int)height, (int)slice, (int)max_bounces, 0, world);
+    const size_t floor_bytes = rt_render_workspace_bytes((int)width, (int)height, 1, (int)max_bounces, 1, world);
+    if (ensure_workspace(d, want, floor_bytes, d.stream)) return 1;
+  }
+  if (n_dev > 1 && g.options.reduce_mode == RT_GPU_REDUCE_NCCL && nccl_prepare()) return 1;
+  CUDA_TRY(cudaSetDevice(g.devs[0].id));
+  return 0;
 }
 
 void rt_gpu_set_options(RT_GPU_Options const *options) {

@@ -13,6 +13,7 @@
 #include <cuda_runtime.h>
 
 #include "rt_kernels.h"
+#include "scene.h"
 
 #define TILE_W 32
 #define TILE_H 8
@@ -102,5 +103,38 @@ int rt_launch_texel_repack(const unsigned char *src, int width, int height, int 
   if (grid > 148u * 16u) grid = 148u * 16u;
   if (grid < 1) grid = 1;
   rt_texel_repack_kernel<<<grid, 256, 0, stream>>>(src, width, height, stride, components, dst);
+  return (int)cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ scene pack
+// Scene upload helper: the per-slot records the kernels read, built on the device from the host's own buffers.
+//   tri_pos[slot] = (p0.xyz, e1.x)(e1.yz, e2.xy)(e2.z, 0, 0, 0) with e1 = p1 - p0, e2 = p2 - p0 — the f32 subtractions
+//                   the reference redoes for every ray (raytracer.c:116-122), done once (IEEE, so the same bits as on the host);
+//   tri_rec[slot] = the first 96 bytes of Triangle_AOS (normal, normal_a/b/c, tangent, bitangent, three UVs: scene.h:46-51)
+//                   as six float4, then the material index in place of the Shader pointer pair.
+__global__ void rt_scene_pack_kernel(const float *__restrict__ soa, const float4 *__restrict__ aos, const int *__restrict__ mat_index,
+                                     int n_slots, float4 *__restrict__ tri_pos, float4 *__restrict__ tri_rec) {
+  const size_t N = (size_t)n_slots;
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n_slots; s += gridDim.x * blockDim.x) {
+    const float p0x = soa[s], p1x = soa[N + s], p2x = soa[2 * N + s];
+    const float p0y = soa[3 * N + s], p1y = soa[4 * N + s], p2y = soa[5 * N + s];
+    const float p0z = soa[6 * N + s], p1z = soa[7 * N + s], p2z = soa[8 * N + s];
+    tri_pos[3 * (size_t)s + 0] = make_float4(p0x, p0y, p0z, __fsub_rn(p1x, p0x));
+    tri_pos[3 * (size_t)s + 1] = make_float4(__fsub_rn(p1y, p0y), __fsub_rn(p1z, p0z), __fsub_rn(p2x, p0x), __fsub_rn(p2y, p0y));
+    tri_pos[3 * (size_t)s + 2] = make_float4(__fsub_rn(p2z, p0z), 0.0f, 0.0f, 0.0f);
+    const float4 *a = aos + 7 * (size_t)s;              // sizeof(Triangle_AOS) == 112 == 7 float4
+    #pragma unroll
+    for (int k = 0; k < 6; k++) tri_rec[7 * (size_t)s + k] = a[k];
+    tri_rec[7 * (size_t)s + 6] = make_float4(__int_as_float(mat_index[s]), 0.0f, 0.0f, 0.0f);
+  }
+}
+
+int rt_launch_scene_pack(const float *soa, const float4 *aos, const int *mat_index, int n_slots, float4 *tri_pos, float4 *tri_rec,
+                         cudaStream_t stream) {
+  static_assert(sizeof(Triangle_AOS) == 112, "Triangle_AOS is seven float4 (scene.h)");
+  unsigned grid = (unsigned)((n_slots + 255) / 256);
+  if (grid > 148u * 8u) grid = 148u * 8u;
+  if (grid < 1) grid = 1;
+  rt_scene_pack_kernel<<<grid, 256, 0, stream>>>(soa, aos, mat_index, n_slots, tri_pos, tri_rec);
   return (int)cudaGetLastError();
 }

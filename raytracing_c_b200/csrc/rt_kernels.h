@@ -29,6 +29,9 @@ int rt_render_blocks_per_sm(void);
 // RGB8 / RGBA8 rows (stride in pixels) -> tightly packed RGBA8 texels
 int rt_launch_texel_repack(const unsigned char *src, int width, int height, int stride, int components,
                            uchar4 *dst, cudaStream_t stream);
+// tri_pos / tri_rec from the host's vertex arrays, Triangle_AOS records and per-slot material indices (rt_denoise.cu)
+int rt_launch_scene_pack(const float *soa, const float4 *aos, const int *mat_index, int n_slots, float4 *tri_pos, float4 *tri_rec,
+                         cudaStream_t stream);
 // per-stage CUDA-event timing of rt_launch_render's kernels (off by default)
 // slot = stage * RT_STAGE_BOUNCES + min(bounce, RT_STAGE_BOUNCES - 1)
 enum { RT_STAGE_TRACE = 0, RT_STAGE_MISS, RT_STAGE_SHADE, RT_STAGE_ACCUMULATE, RT_N_STAGES, RT_STAGE_BOUNCES = 16 };

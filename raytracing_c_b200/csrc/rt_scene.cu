@@ -141,9 +141,13 @@ static int h2d(Device &d, DeviceScene &ds, void *dst, const void *src, size_t n)
 
 // ---------------------------------------------------------------- host-side flattening (once per upload)
 struct HostScene {
-  std::vector<float>       nodes;
-  std::vector<float4>      tri_pos, records;
-  std::vector<float>       tri_soa;
+  // geometry goes up from the host's own buffers (in-place DMA when they are pinned); what the host has to compute
+  // is one material index per triangle slot — the per-slot regrouping is rt_scene_pack_kernel's job on the device
+  const float             *nodes = nullptr;        // scene->bvh.nodes.data, n_internal * 48 floats
+  const float             *soa = nullptr;          // nine vertex arrays of n_slots floats, one block
+  std::vector<float>       soa_copy;               // only if the host's nine arrays are not one block
+  const Triangle_AOS      *aos = nullptr;
+  std::vector<int>         mat_index;              // [n_slots]
   std::vector<MaterialDev> materials;
   std::vector<const Image *> images;
   int   env_slot = -1;
@@ -170,30 +174,26 @@ static int flatten(const Scene *scene, HostScene &hs) {
   hs.fp = fingerprint(scene);
   hs.depth = (int)depth; hs.n_internal = (int)n_nodes; hs.n_slots = (int)n_slots;
 
-  hs.nodes.resize((size_t)n_nodes * 48);
-  memcpy(hs.nodes.data(), scene->bvh.nodes.data, hs.nodes.size() * sizeof(float));
-
-  // per slot: p0.xyz, e1 = p1 - p0, e2 = p2 - p0.  The two edge vectors are the f32 subtractions the reference
-  // redoes for every ray (raytracer.c:116-122); volatile keeps the host compiler from doing them in any wider type
-  hs.tri_pos.resize((size_t)n_slots * 3);
-  const float *px[3] = { scene->triangles.x[0], scene->triangles.y[0], scene->triangles.z[0] };
-  const float *p1[3] = { scene->triangles.x[1], scene->triangles.y[1], scene->triangles.z[1] };
-  const float *p2[3] = { scene->triangles.x[2], scene->triangles.y[2], scene->triangles.z[2] };
-  for (isize s = 0; s < n_slots; s++) {
-    volatile float e1[3], e2[3];
-    for (int a = 0; a < 3; a++) { e1[a] = p1[a][s] - px[a][s]; e2[a] = p2[a][s] - px[a][s]; }
-    hs.tri_pos[(size_t)s * 3 + 0] = make_float4(px[0][s], px[1][s], px[2][s], e1[0]);
-    hs.tri_pos[(size_t)s * 3 + 1] = make_float4(e1[1], e1[2], e2[0], e2[1]);
-    hs.tri_pos[(size_t)s * 3 + 2] = make_float4(e2[2], 0.0f, 0.0f, 0.0f);
-  }
-
-  // the vertex arrays as they are (lightmap_bake interpolates positions from the three vertices, raytracer.c:749-753)
-  hs.tri_soa.resize((size_t)n_slots * 9);
+  hs.nodes = reinterpret_cast<const float *>(scene->bvh.nodes.data);
+  hs.aos = scene->triangles.aos;
+  // scene_init lays the nine vertex arrays out as one block x0 x1 x2 y0 y1 y2 z0 z1 z2 (scene.h:62-63, scene.c:86-96);
+  // a host that assembled them differently gets them gathered into that order
   {
     const float *arrays[9] = { scene->triangles.x[0], scene->triangles.x[1], scene->triangles.x[2],
                                scene->triangles.y[0], scene->triangles.y[1], scene->triangles.y[2],
                                scene->triangles.z[0], scene->triangles.z[1], scene->triangles.z[2] };
-    for (int a = 0; a < 9; a++) memcpy(hs.tri_soa.data() + (size_t)a * (size_t)n_slots, arrays[a], (size_t)n_slots * sizeof(float));
+    bool one_block = true;
+    for (int a = 0; a < 9; a++) one_block &= arrays[a] == arrays[0] + (size_t)a * (size_t)n_slots;
+    if (one_block) {
+      hs.soa = arrays[0];
+    } else {
+      hs.soa_copy.resize((size_t)n_slots * 9);
+      for (int a = 0; a < 9; a++) {
+        if (!arrays[a]) return fail("scene: null vertex array");
+        memcpy(hs.soa_copy.data() + (size_t)a * (size_t)n_slots, arrays[a], (size_t)n_slots * sizeof(float));
+      }
+      hs.soa = hs.soa_copy.data();
+    }
   }
 
   // materials / textures, de-duplicated by host pointer
@@ -208,15 +208,21 @@ static int flatten(const Scene *scene, HostScene &hs) {
     return slot;
   };
 
-  hs.records.resize((size_t)n_slots * 7);
+  hs.mat_index.assign((size_t)n_slots, 0);
+  const void *last_data = nullptr;
+  int last_mat = 0;
+  Shader_Proc last_proc = nullptr;
   for (isize s = 0; s < n_slots; s++) {
     const Triangle_AOS &a = scene->triangles.aos[s];
-    int mat = 0;
-    if (a.shader.proc || a.shader.data) {
+    if (!a.shader.proc && !a.shader.data) continue;
+    if (a.shader.proc != last_proc) {
       bool known = false;
       for (Shader_Proc p : g.pbr_procs) known |= (p == a.shader.proc);
       if (!known) return fail("scene: triangle slot %ld uses a Shader_Proc that was not registered with rt_gpu_register_pbr_shader", (long)s);
-      if (!a.shader.data) return fail("scene: triangle slot %ld has a registered Shader_Proc but no PBR_Shader_Data", (long)s);
+      last_proc = a.shader.proc;
+    }
+    if (!a.shader.data) return fail("scene: triangle slot %ld has a registered Shader_Proc but no PBR_Shader_Data", (long)s);
+    if (a.shader.data != last_data) {
       auto it = material_index.find(a.shader.data);
       if (it == material_index.end()) {
         const PBR_Shader_Data *m = static_cast<const PBR_Shader_Data *>(a.shader.data);
@@ -228,23 +234,15 @@ static int flatten(const Scene *scene, HostScene &hs) {
         d.tex_normal = texture_slot(m->texture_normal);
         d.tex_mr = texture_slot(m->texture_metal_roughness);
         d.tex_emission = texture_slot(m->texture_emission);
-        mat = (int)hs.materials.size();
+        last_mat = (int)hs.materials.size();
         hs.materials.push_back(d);
-        material_index[a.shader.data] = mat;
+        material_index[a.shader.data] = last_mat;
       } else {
-        mat = it->second;
+        last_mat = it->second;
       }
+      last_data = a.shader.data;
     }
-    float4 *r = &hs.records[(size_t)s * 7];
-    r[0] = make_float4(a.normal.x, a.normal.y, a.normal.z, a.normal_a.x);
-    r[1] = make_float4(a.normal_a.y, a.normal_a.z, a.normal_b.x, a.normal_b.y);
-    r[2] = make_float4(a.normal_b.z, a.normal_c.x, a.normal_c.y, a.normal_c.z);
-    r[3] = make_float4(a.tangent.x, a.tangent.y, a.tangent.z, a.bitangent.x);
-    r[4] = make_float4(a.bitangent.y, a.bitangent.z, a.tex_coords_a.x, a.tex_coords_a.y);
-    r[5] = make_float4(a.tex_coords_b.x, a.tex_coords_b.y, a.tex_coords_c.x, a.tex_coords_c.y);
-    float as_float;
-    memcpy(&as_float, &mat, 4);
-    r[6] = make_float4(as_float, 0, 0, 0);
+    hs.mat_index[(size_t)s] = last_mat;
   }
   if (hs.materials.empty()) hs.materials.push_back(MaterialDev{});
 
@@ -262,7 +260,7 @@ static int flatten(const Scene *scene, HostScene &hs) {
   // union of the root's child boxes; all-zero padding slots (lo == hi) can never be entered (enter >= leave)
   for (int a = 0; a < 3; a++) { hs.root_lo[a] = INFINITY; hs.root_hi[a] = -INFINITY; }
   for (int j = 0; j < 8; j++) {
-    const float *n0 = hs.nodes.data();
+    const float *n0 = hs.nodes;
     bool empty = true;
     for (int a = 0; a < 3; a++) empty &= (n0[a * 8 + j] == n0[(3 + a) * 8 + j]);
     if (empty) continue;
@@ -303,14 +301,14 @@ static ArenaLayout layout_of(const HostScene &hs) {
   size_t off = 0;
   L.env = off;
   if (hs.env_slot >= 0) { L.texel_off[(size_t)hs.env_slot] = off; off = align256(off + texel_bytes((size_t)hs.env_slot)); }
-  L.nodes = off;     off = align256(off + hs.nodes.size() * sizeof(float));
-  L.tri_pos = off;   off = align256(off + hs.tri_pos.size() * sizeof(float4));
-  L.tri_rec = off;   off = align256(off + hs.records.size() * sizeof(float4));
+  L.nodes = off;     off = align256(off + (size_t)hs.n_internal * 48 * sizeof(float));
+  L.tri_pos = off;   off = align256(off + (size_t)hs.n_slots * 3 * sizeof(float4));
+  L.tri_rec = off;   off = align256(off + (size_t)hs.n_slots * 7 * sizeof(float4));
   L.materials = off; off = align256(off + hs.materials.size() * sizeof(MaterialDev));
-  L.tri_soa = off;   off = align256(off + hs.tri_soa.size() * sizeof(float));
+  L.tri_soa = off;   off = align256(off + (size_t)hs.n_slots * 9 * sizeof(float));
   L.hot_end = off;
   L.table = off;     off = align256(off + hs.images.size() * sizeof(TextureDev) + 16);
-  L.nodes_rel = off; off = align256(off + hs.nodes.size() * sizeof(float));
+  L.nodes_rel = off; off = align256(off + (size_t)hs.n_internal * 48 * sizeof(float));
   L.tri_rel = off;   off = align256(off + (size_t)hs.n_slots * 4 * sizeof(float4));
   L.texels_begin = off;
   for (size_t i = 0; i < hs.images.size(); i++) {
@@ -353,17 +351,9 @@ static int upload_primary(Device &d, const HostScene &hs, const ArenaLayout &L, 
   char *base = static_cast<char *>(arena);
   std::vector<TextureDev> table;
   bind_arena(base, L, hs, ds, table);
-  if (h2d(d, ds, base + L.nodes, hs.nodes.data(), hs.nodes.size() * sizeof(float))) return 1;
-  if (h2d(d, ds, base + L.tri_pos, hs.tri_pos.data(), hs.tri_pos.size() * sizeof(float4))) return 1;
-  if (h2d(d, ds, base + L.tri_rec, hs.records.data(), hs.records.size() * sizeof(float4))) return 1;
-  if (h2d(d, ds, base + L.materials, hs.materials.data(), hs.materials.size() * sizeof(MaterialDev))) return 1;
-  if (h2d(d, ds, base + L.tri_soa, hs.tri_soa.data(), hs.tri_soa.size() * sizeof(float))) return 1;
-  if (h2d(d, ds, base + L.table, table.data(), table.size() * sizeof(TextureDev))) return 1;
-  CUDA_TRY(cudaEventRecord(ds.geom_ready, d.copy));
-  // texels: raw rows go up as they are (3 B per texel for RGB8); the RGBA8 layout the samplers read (one 32-bit load
-  // per tap) is produced by a kernel on the same stream.  The environment goes first: the miss kernel of bounce 0 is
-  // its first consumer.  Two raw staging blocks alternate, so the DMA of one image overlaps the repack of the previous.
-  size_t raw_max = 0;
+  // raw block = the larger of: every image's raw rows, the Triangle_AOS records + material indices awaiting the pack kernel
+  const size_t aos_bytes = (size_t)hs.n_slots * sizeof(Triangle_AOS), idx_bytes = (size_t)hs.n_slots * sizeof(int);
+  size_t raw_max = align256(aos_bytes) + idx_bytes;
   for (const Image *im : hs.images) {
     const size_t raw = im->pixel_type == PT_RT_JPEG_BYTES ? (size_t)im->width * (size_t)im->height * 3
                                                           : (size_t)im->stride * (size_t)im->height * (size_t)im->components;
@@ -373,6 +363,23 @@ static int upload_primary(Device &d, const HostScene &hs, const ArenaLayout &L, 
     CUDA_TRY(cudaStreamSynchronize(d.copy));
     if (grow(&d.d_texel_stage, &d.texel_stage_bytes, raw_max)) return 1;
   }
+  char *raw_block = static_cast<char *>(d.d_texel_stage);
+  if (h2d(d, ds, base + L.nodes, hs.nodes, (size_t)hs.n_internal * 48 * sizeof(float))) return 1;
+  if (h2d(d, ds, base + L.tri_soa, hs.soa, (size_t)hs.n_slots * 9 * sizeof(float))) return 1;
+  if (h2d(d, ds, raw_block, hs.aos, aos_bytes)) return 1;
+  if (h2d(d, ds, raw_block + align256(aos_bytes), hs.mat_index.data(), idx_bytes)) return 1;
+  if (h2d(d, ds, base + L.materials, hs.materials.data(), hs.materials.size() * sizeof(MaterialDev))) return 1;
+  if (h2d(d, ds, base + L.table, table.data(), table.size() * sizeof(TextureDev))) return 1;
+  {
+    int e = rt_launch_scene_pack(reinterpret_cast<const float *>(base + L.tri_soa), reinterpret_cast<const float4 *>(raw_block),
+                                 reinterpret_cast<const int *>(raw_block + align256(aos_bytes)), hs.n_slots,
+                                 reinterpret_cast<float4 *>(base + L.tri_pos), reinterpret_cast<float4 *>(base + L.tri_rec), d.copy);
+    if (e) return fail("scene pack launch failed: %s", cudaGetErrorString((cudaError_t)e));
+  }
+  CUDA_TRY(cudaEventRecord(ds.geom_ready, d.copy));
+  // texels: raw rows go up as they are (3 B per texel for RGB8); the RGBA8 layout the samplers read (one 32-bit load
+  // per tap) is produced by a kernel on the same stream.  The environment goes first: the miss kernel of bounce 0 is
+  // its first consumer.  Two raw staging blocks alternate, so the DMA of one image overlaps the repack of the previous.
   bool any_jpeg = false;
   for (const Image *im : hs.images) any_jpeg |= im->pixel_type == PT_RT_JPEG_BYTES;
   if (any_jpeg && jpeg_begin_batch(d.copy)) return 1;

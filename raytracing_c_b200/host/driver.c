@@ -111,10 +111,11 @@ static bool parse_args(int argc, char **argv, Config *c) {
   return true;
 }
 
-typedef struct { int n; int *devices; int status; int joined; f64 done_ms; } Init_Job;
+typedef struct { int n; int *devices; int status; int joined; f64 done_ms; isize width, height, samples, bounces; } Init_Job;
 static void *init_entry(void *p) {
   Init_Job *job = p;
   job->status = rt_gpu_init_devices(job->n, job->devices);
+  if (!job->status) rt_gpu_prepare_frame(job->width, job->height, job->samples, job->bounces);      /* best effort */
   job->done_ms = now_ms();
   return NULL;
 }
@@ -140,7 +141,15 @@ int main(int argc, char **argv) {
   }
   /* CUDA context creation (1-2 s) runs on its own thread while this one loads the model, decodes the textures and
    * builds the BVH; pinned host buffers need the context, so --pinned 1 waits for it first */
-  Init_Job init = { config.gpus, devices, 0, 0, 0 };
+  /* options first: they need no device, and the init thread sizes its allocations by them */
+  RT_GPU_Options options;
+  rt_gpu_get_options(&options);
+  options.user_seed = config.seed;
+  options.split_mode = config.split_mode;
+  options.reduce_mode = config.reduce_mode;
+  options.keep_hit_ids = config.dump_hit_ids != NULL;
+  rt_gpu_set_options(&options);
+  Init_Job init = { config.gpus, devices, 0, 0, 0, config.width, config.height, config.samples, config.max_bounces };
   pthread_t init_thread;
   pthread_create(&init_thread, NULL, init_entry, &init);
   if (config.pinned) {
@@ -206,13 +215,6 @@ int main(int argc, char **argv) {
   if (config.verbose)
     printf("GPU init %ldms (on its own thread, beside the model load), model load + texture decode %ldms, scene upload issued in %ldms\n", (long)(t_init_done - t_process),
            (long)(t_load_done - t_load), (long)(now_ms() - t_upload));
-  RT_GPU_Options options;
-  rt_gpu_get_options(&options);
-  options.user_seed = config.seed;
-  options.split_mode = config.split_mode;
-  options.reduce_mode = config.reduce_mode;
-  options.keep_hit_ids = config.dump_hit_ids != NULL;
-  rt_gpu_set_options(&options);
 
   f64 t_render = now_ms();
   Rendering_Context ctx;
