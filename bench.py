@@ -2,19 +2,22 @@
 """bench.py — Msamples/s (pixel*spp/s) of the path-tracing hot path on helmet.glb 1920x1080.
 
     python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path
-    python bench.py --impl reference --steps K --warmup W    # the CPU restatement on the host cores
+    python bench.py --impl reference --steps K --warmup W    # the reference's own CPU renderer on the host cores
 
-A step = one full frame of BASELINE.json's headline config (helmet.glb, 1920x1080, 1024 spp,
-8 bounces, synthetic environment) rendered by N GPUs: every rank renders spp/N samples of every
-pixel into an f32 accumulator (spp-range split), the accumulators are summed to rank 0
-with one NCCL reduce, rank 0 resolves to u8 sRGB.  The total work is fixed => "scaling": "strong".
+A step = one full frame of BASELINE.json's headline config (helmet.glb, 1920x1080, 1024 spp, 8 bounces, synthetic
+environment) rendered by N GPUs, one process per GPU: every rank renders the share of the frame the library's policy
+gives it (rt_gpu_render_shard_device: sample ranges, or the reference's 32x32 chunks when the sample batches do not
+divide evenly), rank 0 combines the f32 accumulators with the library's fused reduce+resolve kernel, which reads the
+peers' buffers in place over NVLink (CUDA IPC; --reduce nccl swaps in an NCCL reduce), and resolves to u8 sRGB.
+The total work is fixed => "scaling": "strong".
 
-Keys beyond the base contract: `roofline` (rt_trace_kernel — BVH traversal, the dominant kernel of
-the wavefront — against the measured FP32 issue ceiling, the bound SURVEY §8d derives: not HBM,
-not tensor; its launch time is measured live with CUDA events around every launch of the timed
-region, rt_gpu_stage_profile_*), `cpu_baseline` (the oracle timed on
-the host cores on a bounded sample), `e2e` (the same frame through the reference entry point
-render_thread_proc with HOST buffers: scene upload H2D and image D2H inside the timed region).
+Keys beyond the base contract: `roofline` (rt_trace_kernel — BVH traversal, the dominant kernel of the wavefront —
+against the measured FP32 issue ceiling, the bound SURVEY 8d derives: not HBM, not tensor; launch time measured live
+with CUDA events around every launch of the timed region; `executed` / `traffic` from the committed ncu capture of the
+same command; `resolve` / `denoise` = the two HBM-streaming kernels), `parity` (rank 0, after the timed region: the
+REDUCED accumulator of the last timed step against the CPU oracle on 4096 random pixels + 4 scanlines at the full sample
+count), `cpu_baseline` (the reference's renderer on the host cores on a bounded sample), `e2e` (the same frame with the
+scene re-uploaded from host memory and the image read back every step, itemised).
 """
 from __future__ import annotations
 

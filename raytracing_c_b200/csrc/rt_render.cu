@@ -66,96 +66,6 @@ __global__ void rt_camera_relative_kernel(const SceneDev sc) {
   }
 }
 
-// ----------------------------------------------------------------------- tail
-// The late bounces carry a few percent of the rays but cost a kernel trio each (trace, miss, shade: 15 launches for
-// bounces 3..7), and every one of those kernels lasts as long as its slowest warp.  This kernel runs the REST of
-// cast_ray's loop (raytracer.c:512-556) for every ray of the RAY queue of bounce P.bounce inside one thread: trace,
-// then environment or BSDF, then the next bounce, with no queue in between.  Same device functions, same order of
-// operations per path — and a path's result depends only on its own record — so the radiance is the same bits.
-__global__ void __launch_bounds__(RT_BLOCK, 2)
-rt_tail_kernel(const __grid_constant__ StageParams P) {
-  extern __shared__ float4 level_store[];
-  __shared__ float texel_lut[256];
-  texel_lut[threadIdx.x] = (float)threadIdx.x / 255.999f;
-  __syncthreads();
-  const SceneDev &sc = P.scene;
-  const unsigned lane = threadIdx.x & 31u;
-  float4 *levels = level_store + threadIdx.x;
-  const unsigned n = P.q.counts[P.bounce * Q_STRIDE + Q_RAYS];
-  unsigned *fetch = &P.q.counts[P.bounce * Q_STRIDE + Q_FETCH];
-  unsigned c_rays = 0, c_nodes = 0, c_leaves = 0, c_accepts = 0, c_root_miss = 0;
-  unsigned c_shades = 0, c_pass = 0, c_samples = 0, c_misses = 0;
-
-  for (;;) {
-    unsigned base = 0;
-    if (lane == 0) base = atomicAdd(fetch, 32u);
-    base = __shfl_sync(RT_FULL, base, 0);
-    if (base >= n) break;
-    const unsigned i = base + lane;
-    bool alive = i < n;
-    V3 o = mk3(0, 0, 0), d = mk3(0, 0, -1), tint = mk3(1, 1, 1), emis = mk3(0, 0, 0);
-    unsigned path = 0;
-    uint32_t rng = 0;
-    if (alive) {
-      const float4 a = P.q.ray_a[i], b = P.q.ray_b[i];
-      o = mk3(a.x, a.y, a.z); d = mk3(a.w, b.x, b.y);
-      path = __float_as_uint(b.z); rng = __float_as_uint(b.w);
-      const float4 c = P.q.tint[path], e = P.q.emis[path];
-      tint = mk3(c.x, c.y, c.z); emis = mk3(e.x, e.y, e.z);
-    }
-    for (int bounce = P.bounce; bounce < P.max_bounces; bounce++) {
-      if (__ballot_sync(RT_FULL, alive) == 0) break;
-      RayWalk w;
-      w.done = true; w.leaf = -1; w.hit_slot = -1;
-      if (alive) {
-        walk_begin(w, sc, o.x, o.y, o.z, d.x, d.y, d.z);
-        c_rays++;
-        if (walk_misses_root<false>(w, sc)) { w.done = true; c_nodes++; c_root_miss++; }
-      }
-      for (;;) {
-        const unsigned want_leaf = __ballot_sync(RT_FULL, w.leaf >= 0);
-        const unsigned want_node = __ballot_sync(RT_FULL, alive && !w.done && w.leaf < 0);
-        if ((want_leaf | want_node) == 0) break;
-        if (__popc(want_node) >= __popc(want_leaf)) {
-          if (want_node >> lane & 1u) walk_node_step<false>(w, sc, levels, c_nodes);
-        } else {
-          walk_leaf<false>(w, sc, c_leaves, c_accepts);
-        }
-        __syncwarp();
-      }
-      if (alive) {
-        if (w.hit_slot < 0) {
-          // raytracer.c:554
-          V3 env = environment(sc, texel_lut, d);
-          V3 radiance = add3(mul3(env, tint), emis);
-          P.q.rad[path] = make_float4(radiance.x, radiance.y, radiance.z, 0);
-          c_misses++; c_samples++;
-          alive = false;
-        } else {
-          bool cont = shade_hit(sc, texel_lut, o, d, tint, emis, rng, w.hit_t, w.hit_u, w.hit_v, w.hit_slot, c_shades, c_pass);
-          if (bounce + 1 >= P.max_bounces) cont = false;      // raytracer.c:557
-          if (!cont) {
-            P.q.rad[path] = make_float4(emis.x, emis.y, emis.z, 0);
-            c_samples++;
-            alive = false;
-          }
-        }
-      }
-    }
-  }
-  if (P.counters) {
-    add_counter(P.counters, 0, c_rays);
-    add_counter(P.counters, 1, c_nodes);
-    add_counter(P.counters, 2, c_leaves);
-    add_counter(P.counters, 3, c_accepts);
-    add_counter(P.counters, 4, c_shades);
-    add_counter(P.counters, 5, c_misses);
-    add_counter(P.counters, 6, c_pass);
-    add_counter(P.counters, 7, c_samples);
-  }
-  if (P.counters_ex) add_counter(P.counters_ex, 0, c_root_miss);
-}
-
 // ----------------------------------------------------------------- accumulate
 // raytracer.c:696-700: color += cast_ray(...) in sample order, one thread per pixel.
 __global__ void __launch_bounds__(256)
@@ -257,9 +167,6 @@ rt_reduce_resolve_kernel(const ReduceParts parts, float *__restrict__ sum_out, i
 // ------------------------------------------------------------------- launchers
 #define RT_PATH_BYTES ((2 + 3 + 1 + 2) * sizeof(float4))       // ray + hit + miss records and the tint / emission(=rad) state of one path
 #define RT_CHUNK_PATHS_MAX (256u << 20)
-#ifndef RT_TAIL_BOUNCE_DEFAULT
-#define RT_TAIL_BOUNCE_DEFAULT (1 << 30)      /* measured slower than the kernel trios (profiles/r02_experiments.md): off */
-#endif
 
 static size_t counts_bytes(int max_bounces) {
   size_t b = (size_t)(max_bounces + 1) * Q_STRIDE * sizeof(unsigned);
@@ -277,15 +184,6 @@ static size_t chunk_paths_max() {
     if (v > 0) return (size_t)v;
   }
   return RT_CHUNK_PATHS_MAX;
-}
-
-// First bounce handled by rt_tail_kernel (all later ones with it); RT_GPU_TAIL_BOUNCE overrides, 0 or >= max_bounces = never.
-static int tail_bounce_setting() {
-  if (const char *e = getenv("RT_GPU_TAIL_BOUNCE")) {
-    const int v = atoi(e);
-    return v > 0 ? v : 1 << 30;
-  }
-  return RT_TAIL_BOUNCE_DEFAULT;
 }
 
 // samples of every pixel per chunk
@@ -386,7 +284,6 @@ static int trace_launch_setup(const SceneDev &scene, int *dev_out, size_t *level
     int n = 0;
     cudaFuncSetAttribute(rt_trace_kernel<true>,  cudaFuncAttributeMaxDynamicSharedMemorySize, RT_MAX_DEPTH * 2 * RT_BLOCK * 16);
     cudaFuncSetAttribute(rt_trace_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RT_MAX_DEPTH * 2 * RT_BLOCK * 16);
-    cudaFuncSetAttribute(rt_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RT_MAX_DEPTH * 2 * RT_BLOCK * 16);
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, rt_trace_kernel<false>, RT_BLOCK, level_bytes) != cudaSuccess || n < 1) n = 1;
     g_trace_blocks_per_sm[dev] = n;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, rt_trace_kernel<true>, RT_BLOCK, level_bytes) != cudaSuccess || n < 1) n = 1;
@@ -440,7 +337,6 @@ int rt_launch_render(const RenderParams &p, int sm_count, void *workspace, size_
   cap = (size_t)chunk * per_sample;
   bind_queues(P.q, static_cast<char *>(workspace), cb, cap);
 
-  const int tail_bounce = tail_bounce_setting();
   rt_camera_relative_kernel<<<(unsigned)sm_count, 256, 0, stream>>>(p.scene);
   const unsigned trace_grid = (unsigned)(sm_count * g_trace_blocks_per_sm[dev]);     // persistent: one wave
   const unsigned primary_grid = (unsigned)(sm_count * g_primary_blocks_per_sm[dev]);
@@ -464,13 +360,6 @@ int rt_launch_render(const RenderParams &p, int sm_count, void *workspace, size_
     for (int b = 0; b < p.max_bounces; b++) {
       P.bounce = b;
       const int bslot = b < RT_STAGE_BOUNCES ? b : RT_STAGE_BOUNCES - 1;
-      if (b >= tail_bounce && b > 0) {
-        // everything from here on in one kernel (timed under the trace stage of this bounce)
-        StageTimer t(RT_STAGE_TRACE * RT_STAGE_BOUNCES + bslot, stream, dev);
-        rt_tail_kernel<<<(unsigned)(sm_count * 2), RT_BLOCK, level_bytes, stream>>>(P);
-        launches++;
-        break;
-      }
       if (b > 0) {
         StageTimer t(RT_STAGE_TRACE * RT_STAGE_BOUNCES + bslot, stream, dev);
         if (p.fast) rt_fast_launch_trace(P, fast_grid, level_bytes, stream);

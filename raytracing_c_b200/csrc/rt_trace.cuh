@@ -220,80 +220,6 @@ __device__ __forceinline__ void walk_node_step(RayWalk &w, const SceneDev &sc, f
 // p0 and the edges e1 = p1 - p0, e2 = p2 - p0 (the same f32 subtractions raytracer.c:116-122
 // does per ray, done once at upload).  Strict <, ascending j: the lowest lane wins a tie
 // inside the leaf and an earlier leaf wins across leaves (raytracer.c:15-32 with eps 0, :159).
-#ifndef RT_LEAF_TWO_PHASE
-#define RT_LEAF_TWO_PHASE 0
-#endif
-// Division-free filter of the u test (raytracer.c:137-141: reject iff u < -eps | u > 1 + eps, u = (1/det) * (tv . pv)).
-// With r = (tv . pv) / det in real numbers, the reference's u is r * (1 + d1) * (1 + d2), |d| <= 2^-24 (one rounded
-// reciprocal, one rounded product).  So r < -eps * (1 + 2e-4) implies u < -eps and r > (1 + eps) * (1 + 2e-4) implies
-// u > 1 + eps whatever the roundings (the margins are a thousand times the error): such a triangle is rejected without
-// the division.  Everything else — NaN and det = 0 included, all compares are false for them — goes to the exact test.
-#define RT_U_LO 1.0002e-4f
-#define RT_U_HI 1.0003f
-__device__ __forceinline__ bool leaf_u_certainly_outside(float det, float un) {
-  const float sun = __uint_as_float(__float_as_uint(un) ^ (__float_as_uint(det) & 0x80000000u));     // un * sign(det)
-  const float adet = fabsf(det);
-  return (sun < -RT_U_LO * adet) | (sun > RT_U_HI * adet);
-}
-
-#if RT_LEAF_TWO_PHASE
-// Two passes over the leaf.  Pass 1, all eight triangles, uniform code: det and tv . pv as the reference computes
-// them (raytracer.c:116-135), the filter above, one candidate bit per triangle.  Pass 2, candidates only, ascending j:
-// the reference's test to the letter.  A warp's lanes hold different candidates, so pass 2 costs as many turns as the
-// lane with most candidates has (typically 1-3), instead of eight turns that each drag the long exact tail along
-// because SOME lane needs it.
-template <bool REL>
-__device__ __forceinline__ void walk_leaf(RayWalk &w, const SceneDev &sc, unsigned &c_leaves, unsigned &c_accepts) {
-  if (w.leaf < 0) return;
-  const float t_before = w.hit_t;
-  c_leaves++;
-  constexpr int STRIDE = REL ? 4 : 3;
-  const float4 *tp = REL ? sc.tri_rel + (size_t)w.leaf * 32 : sc.tri_pos + (size_t)w.leaf * 24;
-  unsigned cand = 0;
-  {
-    float4 A = __ldg(tp), B = __ldg(tp + 1), C = __ldg(tp + 2);
-    #pragma unroll 1
-    for (int j = 0; j < 8; j++) {
-      const float4 *next = tp + STRIDE * (j < 7 ? j + 1 : 7);
-      const float4 An = __ldg(next), Bn = __ldg(next + 1), Cn = __ldg(next + 2);
-      const float e1x = A.w, e1y = B.x, e1z = B.y, e2x = B.z, e2y = B.w, e2z = C.x;
-      const float pvx = w.dy * e2z - w.dz * e2y, pvy = w.dz * e2x - w.dx * e2z, pvz = w.dx * e2y - w.dy * e2x;
-      const float det = e1x * pvx + e1y * pvy + e1z * pvz;
-      const float tvx = REL ? A.x : w.ox - A.x, tvy = REL ? A.y : w.oy - A.y, tvz = REL ? A.z : w.oz - A.z;
-      const float un = tvx * pvx + tvy * pvy + tvz * pvz;
-      cand |= leaf_u_certainly_outside(det, un) ? 0u : (1u << j);
-      A = An; B = Bn; C = Cn;
-    }
-  }
-  while (cand) {
-    const int j = __ffs(cand) - 1;
-    cand &= cand - 1;
-    const float4 *t3 = tp + STRIDE * j;
-    const float4 A = __ldg(t3), B = __ldg(t3 + 1), C = __ldg(t3 + 2);
-    const float e1x = A.w, e1y = B.x, e1z = B.y, e2x = B.z, e2y = B.w, e2z = C.x;
-    float pvx = w.dy * e2z - w.dz * e2y, pvy = w.dz * e2x - w.dx * e2z, pvz = w.dx * e2y - w.dy * e2x;
-    float det = e1x * pvx + e1y * pvy + e1z * pvz;
-    float inv_det = 1.0f / det;
-    float tvx = REL ? A.x : w.ox - A.x, tvy = REL ? A.y : w.oy - A.y, tvz = REL ? A.z : w.oz - A.z;
-    float u = inv_det * (tvx * pvx + tvy * pvy + tvz * pvz);
-    if (!((u < -RT_EPS) | (u > 1 + RT_EPS))) {
-      float qvx, qvy, qvz, tq;
-      if (REL) { qvx = C.y; qvy = C.z; qvz = C.w; tq = __ldg(&t3[3].x); }
-      else {
-        qvx = tvy * e1z - tvz * e1y; qvy = tvz * e1x - tvx * e1z; qvz = tvx * e1y - tvy * e1x;
-        tq = e2x * qvx + e2y * qvy + e2z * qvz;
-      }
-      float v = inv_det * (w.dx * qvx + w.dy * qvy + w.dz * qvz);
-      float t = inv_det * tq;
-      bool miss = (v < -RT_EPS) | (u + v > 1 + RT_EPS) | (t < RT_EPS);
-      // t <= 0 and NaN count as +inf (min_f32x8 with eps 0); NaN also fails the ordered compare
-      if (!miss && t > 0.0f && t < w.hit_t) { w.hit_t = t; w.hit_u = u; w.hit_v = v; w.hit_slot = w.leaf * 8 + j; }
-    }
-  }
-  if (w.hit_t < t_before) c_accepts++;
-  w.leaf = -1;
-}
-#else
 template <bool REL>
 __device__ __forceinline__ void walk_leaf(RayWalk &w, const SceneDev &sc, unsigned &c_leaves, unsigned &c_accepts) {
   if (w.leaf < 0) return;
@@ -342,4 +268,3 @@ __device__ __forceinline__ void walk_leaf(RayWalk &w, const SceneDev &sc, unsign
   if (w.hit_t < t_before) c_accepts++;
   w.leaf = -1;
 }
-#endif
