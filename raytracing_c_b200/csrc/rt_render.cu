@@ -315,6 +315,9 @@ int rt_launch_render(const RenderParams &p, int sm_count, void *workspace, size_
   P.split_rank = p.split_rank; P.split_world = p.split_world > 1 ? p.split_world : 1;
   P.chunks_x = (p.width + 31) / 32;
   P.n_tiles = rt_render_tiles(p.width, p.height, P.split_rank, P.split_world);
+  // a path id is at most n_paths (32-bit), so a tile id is below 2^27 and a chunk id below tiles/32 * world + world
+  P.div_tiles_x = rt_fastdiv_make((uint32_t)P.tiles_x, 0xffffffffu >> 5);
+  P.div_chunks_x = rt_fastdiv_make((uint32_t)P.chunks_x, 0xffffffffu);
   P.max_bounces = p.max_bounces;
   P.user_seed = p.user_seed;
   P.accum = p.accum;
@@ -347,6 +350,7 @@ int rt_launch_render(const RenderParams &p, int sm_count, void *workspace, size_
     const int S = (p.sample_end - s0 < chunk) ? p.sample_end - s0 : chunk;
     P.sample0 = s0; P.n_samples = S;
     P.n_paths = (unsigned)(per_sample * (size_t)S);
+    P.div_samples = rt_fastdiv_make((uint32_t)S, P.n_paths);
     P.accumulate = (p.accumulate || s0 > p.sample_begin || P.split_world > 1) ? 1 : 0;
     P.per_sample_offset = s0 - p.sample_begin;
     P.hit_ids = (s0 == p.sample_begin) ? p.hit_ids : nullptr;

@@ -10,6 +10,7 @@
 #include <math_constants.h>
 
 #include "rt_device.cuh"
+#include "rt_fastdiv.h"
 #include "rt_trace.cuh"
 #include "rt_shade.cuh"
 
@@ -55,6 +56,7 @@ struct StageParams {
   int        bounce, max_bounces;
   uint32_t   user_seed;
   unsigned   n_paths;                 // tiles * n_samples * 32
+  RT_FastDiv div_samples, div_tiles_x, div_chunks_x;   // magic pairs of the three per-launch divisors (rt_fastdiv.h)
   int        accumulate;
   float     *accum;
   float     *per_sample;              // optional [pixel][per_sample_stride][3], this chunk at +per_sample_offset
@@ -79,12 +81,14 @@ __device__ __forceinline__ float hash12(float px, float py) {
 // tile's place inside the k-th 32x32 chunk this rank owns (chunk id = k * split_world + split_rank)
 __device__ __forceinline__ void tile_origin(const StageParams &P, unsigned tile, int &x0, int &y0) {
   if (P.split_world <= 1) {
-    x0 = (int)(tile % (unsigned)P.tiles_x) * 8;
-    y0 = (int)(tile / (unsigned)P.tiles_x) * 4;
+    const unsigned row = rt_fastdiv(tile, P.div_tiles_x, (unsigned)P.tiles_x);
+    x0 = (int)(tile - row * (unsigned)P.tiles_x) * 8;
+    y0 = (int)row * 4;
   } else {
     const unsigned chunk = (tile >> 5) * (unsigned)P.split_world + (unsigned)P.split_rank, t = tile & 31u;
-    x0 = (int)(chunk % (unsigned)P.chunks_x) * 32 + (int)(t & 3u) * 8;
-    y0 = (int)(chunk / (unsigned)P.chunks_x) * 32 + (int)(t >> 2) * 4;      // beyond the last chunk row: y0 >= height
+    const unsigned row = rt_fastdiv(chunk, P.div_chunks_x, (unsigned)P.chunks_x);
+    x0 = (int)(chunk - row * (unsigned)P.chunks_x) * 32 + (int)(t & 3u) * 8;
+    y0 = (int)row * 32 + (int)(t >> 2) * 4;                                 // beyond the last chunk row: y0 >= height
   }
 }
 
@@ -96,7 +100,7 @@ __device__ __forceinline__ void tile_origin(const StageParams &P, unsigned tile,
 #endif
 __device__ __forceinline__ void path_pixel(const StageParams &P, unsigned path, int &px, int &py, int &ls) {
 #if RT_PATH_LAYOUT == 1
-  const unsigned pix = path / (unsigned)P.n_samples;
+  const unsigned pix = rt_fastdiv(path, P.div_samples, (unsigned)P.n_samples);
   ls = (int)(path - pix * (unsigned)P.n_samples);
   const unsigned in_tile = pix & 31u, tile = pix >> 5;
 #else
@@ -165,8 +169,8 @@ RT_KN(rt_trace_kernel)(const __grid_constant__ StageParams P) {
   const float aspect = (float)P.width / (float)P.height;
 
   RayWalk w;
-  w.done = true; w.leaf = -1;
-  bool     has_ray = false, exhausted = false;
+  w.flags = 0; w.leaf = -1; w.hit_slot = -1;
+  bool     exhausted = false;
   unsigned q = 0, range_next = 0, range_end = 0;
   uint32_t seed0 = 0;                      // primary: the path's RNG seed, fixed when the ray is generated
   // rays reserved per atomic: large queues amortise the round trip, small ones (late bounces)
@@ -181,17 +185,17 @@ RT_KN(rt_trace_kernel)(const __grid_constant__ StageParams P) {
     if (batch > 32u) batch = 32u;
   }
 
+  unsigned walking = 0;                    // lanes whose walk is not finished (WALK_LIVE), kept current across turns
   for (;;) {
-    const unsigned walking = __ballot_sync(RT_FULL, has_ray && !w.done);
     if (walking == 0 || (!exhausted && __popc(~walking) >= (PRIMARY ? RT_REFILL_MIN_PRIMARY : RT_REFILL_MIN_BOUNCE))) {
       // ---- emit: finished lanes hand their path to the next stage
-      const bool fin = has_ray;        // every lane that is not walking and holds a ray has finished it
-      const bool is_hit = fin && !(walking >> lane & 1u) && w.hit_slot >= 0;
-      const bool is_miss = fin && !(walking >> lane & 1u) && w.hit_slot < 0;
-      if (__any_sync(RT_FULL, is_hit | is_miss)) {
+      const bool fin = (w.flags & (WALK_RAY | WALK_LIVE)) == WALK_RAY;
+      const bool is_hit = fin && w.hit_slot >= 0;
+      const bool is_miss = fin && w.hit_slot < 0;
+      if (__any_sync(RT_FULL, fin)) {
         unsigned path = q;
         uint32_t rng = seed0;
-        if (is_hit | is_miss) {
+        if (fin) {
           if (PRIMARY) {
             if (P.hit_ids) {                       // parity hook: primary-hit slot of the chunk's first sample
               int px, py, ls;
@@ -214,7 +218,7 @@ RT_KN(rt_trace_kernel)(const __grid_constant__ StageParams P) {
         if (is_miss) {
           P.q.miss_a[mpos] = make_float4(w.dx, w.dy, w.dz, __uint_as_float(path));
         }
-        if (is_hit | is_miss) has_ray = false;
+        if (fin) w.flags = 0;
       }
       // ---- refill: lanes that are not walking take the next rays of the warp's reserved range;
       // a warp reserves `batch` consecutive rays per atomic (one round trip per batch, not per refill)
@@ -264,17 +268,18 @@ RT_KN(rt_trace_kernel)(const __grid_constant__ StageParams P) {
           }
           if (ok) {
             walk_begin(w, sc, ox, oy, oz, dx, dy, dz);
-            has_ray = true;
             c_rays++;
-            if (walk_misses_root<PRIMARY>(w, sc)) { w.done = true; c_nodes++; c_root_miss++; }      // the root visit, nothing entered
+            if (walk_misses_root<PRIMARY>(w, sc)) { w.flags = WALK_RAY; c_nodes++; c_root_miss++; }      // the root visit, nothing entered
           }
         }
         range_next += take;
       }
-      if (__ballot_sync(RT_FULL, has_ray) == 0) {
-        // nothing taken: the queue is drained — or (chunk split) the 32 ids just taken were a job tile that lies
-        // outside the image, and the warp's reserved range goes on
-        if (exhausted) break;
+      walking = __ballot_sync(RT_FULL, w.flags & WALK_LIVE);
+      if (walking == 0) {
+        // nobody walks: rays that finished at their root visit go out on the next turn; with none of those either
+        // the queue is drained — or (chunk split) the 32 ids just taken were a job tile that lies outside the
+        // image, and the warp's reserved range goes on
+        if (exhausted && __ballot_sync(RT_FULL, w.flags & WALK_RAY) == 0) break;
         continue;
       }
     }
@@ -283,21 +288,20 @@ RT_KN(rt_trace_kernel)(const __grid_constant__ StageParams P) {
       // coherent rays reach their leaves in nearly the same number of steps: plain while-while — every
       // lane walks until it holds a leaf (or is done), then the warp tests the triangles together
       // (measured 2.8 % faster than voting for them)
-      while (has_ray && !w.done && w.leaf < 0) walk_node_step<PRIMARY>(w, sc, levels, c_nodes);
+      while ((w.flags & (WALK_LIVE | WALK_LEAF)) == WALK_LIVE) walk_node_step<PRIMARY>(w, sc, levels, c_nodes);
       __syncwarp();
-      walk_leaf<PRIMARY>(w, sc, c_leaves, c_accepts);
+      if (w.flags & WALK_LEAF) walk_leaf<PRIMARY>(w, sc, c_leaves, c_accepts);
     } else {
       // incoherent rays: one step for the majority — node steps and leaf tests are different code, so the
       // warp runs whichever more lanes wait for and the others keep their state for a later turn
-      const unsigned want_leaf = __ballot_sync(RT_FULL, w.leaf >= 0);
-      const unsigned want_node = __ballot_sync(RT_FULL, has_ray && !w.done && w.leaf < 0);
-      if (__popc(want_node) >= __popc(want_leaf)) {
-        if (want_node >> lane & 1u) walk_node_step<PRIMARY>(w, sc, levels, c_nodes);
+      const unsigned want_leaf = __ballot_sync(RT_FULL, w.flags & WALK_LEAF);
+      if (2 * __popc(want_leaf) <= __popc(walking)) {        // node steps wanted by at least as many lanes
+        if ((w.flags & (WALK_LIVE | WALK_LEAF)) == WALK_LIVE) walk_node_step<PRIMARY>(w, sc, levels, c_nodes);
       } else {
-        walk_leaf<PRIMARY>(w, sc, c_leaves, c_accepts);
+        if (w.flags & WALK_LEAF) walk_leaf<PRIMARY>(w, sc, c_leaves, c_accepts);
       }
     }
-    __syncwarp();
+    walking = __ballot_sync(RT_FULL, w.flags & WALK_LIVE);
   }
 
   if (P.counters) {
