@@ -1,0 +1,16 @@
+"""include/rt_fastdiv.h: the multiply-high division the primary trace uses for path id -> (pixel, sample) and
+tile -> (x, y) must equal `/` for every dividend of the range it was made for (exhaustive for small ranges,
+strided plus every multiple-of-d boundary for the large ones)."""
+import os
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_fastdiv_equals_division(tmp_path):
+    exe = tmp_path / "fastdiv_check"
+    subprocess.run(["gcc", "-O2", "-I", os.path.join(ROOT, "include"), "-o", str(exe),
+                    os.path.join(ROOT, "tests", "csrc", "fastdiv_check.c")], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout
+    assert out.stdout.strip().endswith("ok")
