@@ -14,3 +14,13 @@ def test_fastdiv_equals_division(tmp_path):
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout
     assert out.stdout.strip().endswith("ok")
+
+
+def test_fma_division_by_1p055_is_the_ieee_quotient(tmp_path):
+    """rt_shade.cuh div_1p055 (sRGB decode): x*r, exact residual, one correction == x / 1.055f for every float in [0.01, 4]."""
+    exe = tmp_path / "div_const_check"
+    subprocess.run(["gcc", "-O2", "-ffp-contract=off", "-mfma", "-o", str(exe),
+                    os.path.join(ROOT, "tests", "csrc", "div_const_check.c"), "-lm"], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout
+    assert out.stdout.strip().endswith("ok")
