@@ -218,7 +218,7 @@ size_t rt_render_workspace_bytes(int width, int height, int n_samples, int max_b
 }
 
 // occupancy of the trace kernel and its dynamic-shared-memory opt-in, per device (cudaFuncSetAttribute is per device)
-static int g_trace_blocks_per_sm[RT_MAX_DEVICES], g_primary_blocks_per_sm[RT_MAX_DEVICES], g_fast_blocks_per_sm[RT_MAX_DEVICES];
+static int g_trace_blocks_per_sm[RT_MAX_DEVICES], g_wide_blocks_per_sm[RT_MAX_DEVICES], g_primary_blocks_per_sm[RT_MAX_DEVICES], g_fast_blocks_per_sm[RT_MAX_DEVICES];
 static size_t g_level_bytes[RT_MAX_DEVICES];
 
 // ---- optional per-stage timing (bench.py's roofline leg): CUDA events around every launch, on the
@@ -288,6 +288,9 @@ static int trace_launch_setup(const SceneDev &scene, int *dev_out, size_t *level
     g_trace_blocks_per_sm[dev] = n;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, rt_trace_kernel<true>, RT_BLOCK, level_bytes) != cudaSuccess || n < 1) n = 1;
     g_primary_blocks_per_sm[dev] = n;
+    cudaFuncSetAttribute(rt_trace_kernel<false, RT_TRACE_MIN_BLOCKS_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, RT_MAX_DEPTH * 2 * RT_BLOCK * 16);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, rt_trace_kernel<false, RT_TRACE_MIN_BLOCKS_WIDE>, RT_BLOCK, level_bytes) != cudaSuccess || n < 1) n = 1;
+    g_wide_blocks_per_sm[dev] = n;
     g_fast_blocks_per_sm[dev] = rt_fast_trace_setup(level_bytes);
     g_level_bytes[dev] = level_bytes;
   }
@@ -342,6 +345,7 @@ int rt_launch_render(const RenderParams &p, int sm_count, void *workspace, size_
 
   rt_camera_relative_kernel<<<(unsigned)sm_count, 256, 0, stream>>>(p.scene);
   const unsigned trace_grid = (unsigned)(sm_count * g_trace_blocks_per_sm[dev]);     // persistent: one wave
+  const unsigned wide_grid = (unsigned)(sm_count * g_wide_blocks_per_sm[dev]);
   const unsigned primary_grid = (unsigned)(sm_count * g_primary_blocks_per_sm[dev]);
   const unsigned fast_grid = (unsigned)(sm_count * g_fast_blocks_per_sm[dev]);
   const unsigned flat_grid  = (unsigned)(sm_count * 8);
@@ -367,6 +371,7 @@ int rt_launch_render(const RenderParams &p, int sm_count, void *workspace, size_
       if (b > 0) {
         StageTimer t(RT_STAGE_TRACE * RT_STAGE_BOUNCES + bslot, stream, dev);
         if (p.fast) rt_fast_launch_trace(P, fast_grid, level_bytes, stream);
+        else if (b <= RT_TRACE_WIDE_BOUNCES) rt_trace_kernel<false, RT_TRACE_MIN_BLOCKS_WIDE><<<wide_grid, RT_BLOCK, level_bytes, stream>>>(P);
         else        rt_trace_kernel<false><<<trace_grid, RT_BLOCK, level_bytes, stream>>>(P);
         launches++;
       }

@@ -26,6 +26,12 @@
 #ifndef RT_TRACE_MIN_BLOCKS_PRIMARY
 #define RT_TRACE_MIN_BLOCKS_PRIMARY 4
 #endif
+#ifndef RT_TRACE_MIN_BLOCKS_WIDE
+#define RT_TRACE_MIN_BLOCKS_WIDE 4       // bounce rays of the first RT_TRACE_WIDE_BOUNCES bounces
+#endif
+#ifndef RT_TRACE_WIDE_BOUNCES
+#define RT_TRACE_WIDE_BOUNCES 2
+#endif
 #define RT_FULL 0xffffffffu
 
 // counts[bounce][...]: queue lengths written by one stage and read by the next
@@ -152,9 +158,12 @@ __device__ __forceinline__ unsigned warp_append(unsigned *count, bool want, unsi
 #define RT_REFILL_MIN_BOUNCE 20
 #endif
 
-template <bool PRIMARY>
-// coherent primary rays gain from a fourth resident block (-2.8 % on their kernel), bounce rays lose 3 % with it
-__global__ void __launch_bounds__(RT_BLOCK, PRIMARY ? RT_TRACE_MIN_BLOCKS_PRIMARY : RT_TRACE_MIN_BLOCKS)
+// MIN_BLOCKS: resident blocks per SM the kernel is compiled for.  Coherent primary rays gain from a fourth block
+// (64 registers; -2.8 % on their kernel).  Bounce rays: the long queues of the first bounces gain too (-2.7 % at
+// bounce 1: more warps to cover the divergent loads), the short late queues lose 5-10 % to it (their time is the
+// slowest ray's latency, which spills lengthen) — the host picks per bounce (rt_render.cu, RT_TRACE_WIDE_BOUNCES).
+template <bool PRIMARY, int MIN_BLOCKS = (PRIMARY ? RT_TRACE_MIN_BLOCKS_PRIMARY : RT_TRACE_MIN_BLOCKS)>
+__global__ void __launch_bounds__(RT_BLOCK, MIN_BLOCKS)
 RT_KN(rt_trace_kernel)(const __grid_constant__ StageParams P) {
   extern __shared__ float4 level_store[];          // [depth][2][RT_BLOCK] entry distances of pending levels
   const SceneDev &sc = P.scene;
