@@ -106,6 +106,23 @@ int rt_launch_texel_repack(const unsigned char *src, int width, int height, int 
   return (int)cudaGetLastError();
 }
 
+// RGBA8 texels -> (r, g, b) / 255.999f as floats (driver.c:69-88: the division the reference does per tap; IEEE, so the
+// same bits as the samplers' 256-entry table holds)
+__global__ void rt_texel_expand_kernel(const uchar4 *__restrict__ src, size_t n, float4 *__restrict__ dst) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const uchar4 t = src[i];
+    dst[i] = make_float4((float)t.x / 255.999f, (float)t.y / 255.999f, (float)t.z / 255.999f, 0.0f);
+  }
+}
+
+int rt_launch_texel_expand(const uchar4 *src, size_t n, float4 *dst, cudaStream_t stream) {
+  unsigned grid = (unsigned)((n + 255) / 256);
+  if (grid > 148u * 16u) grid = 148u * 16u;
+  if (grid < 1) grid = 1;
+  rt_texel_expand_kernel<<<grid, 256, 0, stream>>>(src, n, dst);
+  return (int)cudaGetLastError();
+}
+
 // ------------------------------------------------------------------ scene pack
 // Scene upload helper: the per-slot records the kernels read, built on the device from the host's own buffers.
 //   tri_pos[slot] = (p0.xyz, e1.x)(e1.yz, e2.xy)(e2.z, 0, 0, 0) with e1 = p1 - p0, e2 = p2 - p0 — the f32 subtractions

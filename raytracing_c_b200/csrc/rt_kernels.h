@@ -29,6 +29,8 @@ int rt_render_blocks_per_sm(void);
 // RGB8 / RGBA8 rows (stride in pixels) -> tightly packed RGBA8 texels
 int rt_launch_texel_repack(const unsigned char *src, int width, int height, int stride, int components,
                            uchar4 *dst, cudaStream_t stream);
+// RGBA8 texels -> float4 (r, g, b, 0) / 255.999f: the environment's second copy (TextureDev.texels_f32)
+int rt_launch_texel_expand(const uchar4 *src, size_t n, float4 *dst, cudaStream_t stream);
 // tri_pos / tri_rec from the host's vertex arrays, Triangle_AOS records and per-slot material indices (rt_denoise.cu)
 int rt_launch_scene_pack(const float *soa, const float4 *aos, const int *mat_index, int n_slots, float4 *tri_pos, float4 *tri_rec,
                          cudaStream_t stream);

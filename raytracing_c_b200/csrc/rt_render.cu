@@ -348,7 +348,13 @@ int rt_launch_render(const RenderParams &p, int sm_count, void *workspace, size_
   const unsigned wide_grid = (unsigned)(sm_count * g_wide_blocks_per_sm[dev]);
   const unsigned primary_grid = (unsigned)(sm_count * g_primary_blocks_per_sm[dev]);
   const unsigned fast_grid = (unsigned)(sm_count * g_fast_blocks_per_sm[dev]);
+  // grid-stride kernels (miss, shade, accumulate): blocks per SM by queue length.  The items of a queue cost unevenly
+  // (texture taps, lobe picks), so the long queues of the first bounces want many short-lived blocks to even out the
+  // last wave (bounce-0 miss 2073 / 1950 / 1889 / 1864 / 1856 us at 8 / 16 / 32 / 64 / 128 blocks per SM), the short late
+  // queues want few (every block builds its texel table first: bounce-7 shade 23 / 31 / 41 us at 8 / 64 / 128).
   const unsigned flat_grid  = (unsigned)(sm_count * 8);
+  auto miss_grid  = [&](int b) { return (unsigned)sm_count * (b == 0 ? 64u : b == 1 ? 32u : 8u); };
+  auto shade_grid = [&](int b) { return (unsigned)sm_count * (b == 0 ? 64u : 8u); };
   int launches = 1;
   for (int s0 = p.sample_begin; s0 < p.sample_end; s0 += chunk) {
     const int S = (p.sample_end - s0 < chunk) ? p.sample_end - s0 : chunk;
@@ -377,17 +383,17 @@ int rt_launch_render(const RenderParams &p, int sm_count, void *workspace, size_
       }
       {
         StageTimer t(RT_STAGE_MISS * RT_STAGE_BOUNCES + bslot, stream, dev);
-        if (p.fast) rt_fast_launch_miss(P, flat_grid, stream);
-        else        rt_miss_kernel<<<flat_grid, 256, 0, stream>>>(P);
+        if (p.fast) rt_fast_launch_miss(P, miss_grid(b), stream);
+        else        rt_miss_kernel<<<miss_grid(b), 256, 0, stream>>>(P);
       }
       {
         StageTimer t(RT_STAGE_SHADE * RT_STAGE_BOUNCES + bslot, stream, dev);
-        if (p.fast) rt_fast_launch_shade(P, flat_grid, stream);
-        else        rt_shade_kernel<<<flat_grid, 256, 0, stream>>>(P);
+        if (p.fast) rt_fast_launch_shade(P, shade_grid(b), stream);
+        else        rt_shade_kernel<<<shade_grid(b), 256, 0, stream>>>(P);
       }
       launches += 2;
     }
-    { StageTimer t(RT_STAGE_ACCUMULATE * RT_STAGE_BOUNCES, stream, dev); rt_accumulate_kernel<<<flat_grid, 256, 0, stream>>>(P); }
+    { StageTimer t(RT_STAGE_ACCUMULATE * RT_STAGE_BOUNCES, stream, dev); rt_accumulate_kernel<<<flat_grid * 4, 256, 0, stream>>>(P); }
     launches++;
   }
   if (n_launches) *n_launches += launches;

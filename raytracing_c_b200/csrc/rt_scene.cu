@@ -286,9 +286,11 @@ static int make_events(DeviceScene &ds) {
 
 // One arena per scene and device (one cudaMalloc, one persisting-L2 window, two peer copies):
 //   [ environment texels | nodes | tri_pos | tri_rec | materials ]  [ texture table ] [ nodes_rel | tri_rel ] [ other texels ]
+//   [ environment texels as floats ]     (built on each device by a kernel, not copied: beyond `total`)
 // The first bracket is what every ray re-reads; the persisting window (set_l2_window) starts there.
 struct ArenaLayout {
   size_t env, nodes, tri_pos, tri_rec, materials, tri_soa, hot_end, table, nodes_rel, tri_rel, texels_begin, total;
+  size_t env_f32, alloc_total;       // total = end of what travels host -> device / device -> device
   std::vector<size_t> texel_off;     // per image slot
 };
 
@@ -317,6 +319,9 @@ static ArenaLayout layout_of(const HostScene &hs) {
     off = align256(off + texel_bytes(i));
   }
   L.total = off;
+  L.env_f32 = off;
+  if (hs.env_slot >= 0) off = align256(off + (size_t)hs.images[(size_t)hs.env_slot]->width * (size_t)hs.images[(size_t)hs.env_slot]->height * sizeof(float4));
+  L.alloc_total = off;
   return L;
 }
 
@@ -334,6 +339,7 @@ static void bind_arena(char *base, const ArenaLayout &L, const HostScene &hs, De
     table[i].texels = reinterpret_cast<const uchar4 *>(base + L.texel_off[i]);
     table[i].width = (int)hs.images[i]->width;
     table[i].height = (int)hs.images[i]->height;
+    table[i].texels_f32 = (int)i == hs.env_slot ? reinterpret_cast<const float4 *>(base + L.env_f32) : nullptr;
   }
   ds.hot_base = base;
   ds.hot_bytes = L.hot_end;
@@ -347,7 +353,7 @@ static int upload_primary(Device &d, const HostScene &hs, const ArenaLayout &L, 
   ds.fp = hs.fp;
   fill_common(hs, ds.dev);
   void *arena = nullptr;
-  if (pool_alloc(d, ds, L.total, &arena)) return 1;
+  if (pool_alloc(d, ds, L.alloc_total, &arena)) return 1;
   char *base = static_cast<char *>(arena);
   std::vector<TextureDev> table;
   bind_arena(base, L, hs, ds, table);
@@ -404,6 +410,11 @@ static int upload_primary(Device &d, const HostScene &hs, const ArenaLayout &L, 
                                  (int)im->stride, im->components, reinterpret_cast<uchar4 *>(base + L.texel_off[i]), d.copy);
     }
     if (e) return fail("texel repack launch failed: %s", cudaGetErrorString((cudaError_t)e));
+    if ((int)i == hs.env_slot) {
+      e = rt_launch_texel_expand(reinterpret_cast<const uchar4 *>(base + L.texel_off[i]), (size_t)im->width * (size_t)im->height,
+                                 reinterpret_cast<float4 *>(base + L.env_f32), d.copy);
+      if (e) return fail("texel expand launch failed: %s", cudaGetErrorString((cudaError_t)e));
+    }
   }
   CUDA_TRY(cudaEventRecord(ds.tex_ready, d.copy));
   return 0;
@@ -417,7 +428,7 @@ static int upload_peer(Device &d, const Device &src_dev, const DeviceScene &src,
   ds.fp = hs.fp;
   fill_common(hs, ds.dev);
   void *arena = nullptr;
-  if (pool_alloc(d, ds, L.total, &arena)) return 1;
+  if (pool_alloc(d, ds, L.alloc_total, &arena)) return 1;
   char *base = static_cast<char *>(arena);
   const char *src_base = static_cast<const char *>(src.blocks[0].p);
   std::vector<TextureDev> table;
@@ -429,7 +440,13 @@ static int upload_peer(Device &d, const Device &src_dev, const DeviceScene &src,
   if (h2d(d, ds, base + L.table, table.data(), table.size() * sizeof(TextureDev))) return 1;      // pointers differ per device
   CUDA_TRY(cudaEventRecord(ds.geom_ready, d.copy));
   CUDA_TRY(cudaStreamWaitEvent(d.copy, src.tex_ready, 0));
-  if (env_bytes) CUDA_TRY(cudaMemcpyPeerAsync(base, d.id, src_base, src_dev.id, env_bytes, d.copy));
+  if (env_bytes) {
+    CUDA_TRY(cudaMemcpyPeerAsync(base, d.id, src_base, src_dev.id, env_bytes, d.copy));
+    const Image *env = hs.images[(size_t)hs.env_slot];
+    int e = rt_launch_texel_expand(reinterpret_cast<const uchar4 *>(base), (size_t)env->width * (size_t)env->height,
+                                   reinterpret_cast<float4 *>(base + L.env_f32), d.copy);
+    if (e) return fail("texel expand launch failed: %s", cudaGetErrorString((cudaError_t)e));
+  }
   if (L.total > L.texels_begin)
     CUDA_TRY(cudaMemcpyPeerAsync(base + L.texels_begin, d.id, src_base + L.texels_begin, src_dev.id, L.total - L.texels_begin, d.copy));
   ds.p2p_bytes += env_bytes + (L.total - L.texels_begin);

@@ -34,6 +34,23 @@ __device__ __forceinline__ float m_asin(float x) { return rt_asinf(x); }
 __device__ __forceinline__ void  m_sincos(float a, float *s, float *c) { rt_sincosf(a, s, c); }
 #endif
 
+// out-of-line pieces of the shading code (experiments: -DRT_SHADE_PBR_INLINE=1, -DRT_ENV_INLINE=1, -DRT_BILINEAR_INLINE=1)
+#if defined(RT_SHADE_PBR_INLINE) && RT_SHADE_PBR_INLINE
+#define RT_SHADE_PBR_FN __device__ __forceinline__
+#else
+#define RT_SHADE_PBR_FN static __device__ __noinline__
+#endif
+#if defined(RT_ENV_INLINE) && RT_ENV_INLINE
+#define RT_ENV_FN __device__ __forceinline__
+#else
+#define RT_ENV_FN static __device__ __noinline__
+#endif
+#if defined(RT_BILINEAR_INLINE) && RT_BILINEAR_INLINE
+#define RT_BILINEAR_FN __device__ __forceinline__
+#else
+#define RT_BILINEAR_FN static __device__ __noinline__
+#endif
+
 struct ShadeIn  { V3 dir, normal, normal_geo, tangent, bitangent; float u, v; };
 struct ShadeOut { V3 dir, tint, emission; bool terminate; };
 
@@ -46,7 +63,7 @@ __device__ __forceinline__ V3 texel_rgb(const TextureDev &tex, const float *lut,
 }
 
 // driver.c:49-93: negative wrap, fract, no half-texel offset, +1 neighbour clamped
-static __device__ __noinline__ V3 sample_bilinear(const TextureDev &tex, const float *lut, float u, float v) {
+RT_BILINEAR_FN V3 sample_bilinear(const TextureDev &tex, const float *lut, float u, float v) {
   if (u < 0) u += (float)(-(int)u + 1);
   if (v < 0) v += (float)(-(int)v + 1);
   u = u - floorf(u);
@@ -57,6 +74,13 @@ static __device__ __noinline__ V3 sample_bilinear(const TextureDev &tex, const f
   float a = px - (float)x0, b = py - (float)y0;
   int x1 = (x0 + 1 < tex.width)  ? x0 + 1 : x0;
   int y1 = (y0 + 1 < tex.height) ? y0 + 1 : y0;
+  if (tex.texels_f32) {                 // the environment: texels already divided (rt_device.cuh)
+    const float4 *row0 = tex.texels_f32 + (size_t)tex.width * y0, *row1 = tex.texels_f32 + (size_t)tex.width * y1;
+    const float4 t00 = __ldg(row0 + x0), t10 = __ldg(row0 + x1), t01 = __ldg(row1 + x0), t11 = __ldg(row1 + x1);
+    V3 top = lerp3(mk3(t00.x, t00.y, t00.z), mk3(t10.x, t10.y, t10.z), a);
+    V3 bot = lerp3(mk3(t01.x, t01.y, t01.z), mk3(t11.x, t11.y, t11.z), a);
+    return lerp3(top, bot, b);
+  }
   V3 top = lerp3(texel_rgb(tex, lut, x0, y0), texel_rgb(tex, lut, x1, y0), a);
   V3 bot = lerp3(texel_rgb(tex, lut, x0, y1), texel_rgb(tex, lut, x1, y1), a);
   return lerp3(top, bot, b);
@@ -83,7 +107,7 @@ __device__ __forceinline__ V3 decode_srgb(V3 c) {
 }
 
 // driver.c:95-104 (asin argument clamped: DESIGN.md deviation list)
-static __device__ __noinline__ V3 environment(const SceneDev &sc, const float *lut, V3 dir) {
+RT_ENV_FN V3 environment(const SceneDev &sc, const float *lut, V3 dir) {
   float inv_pi     = (float)(1.0f / RT_PI_R);
   float inv_two_pi = (float)(1.0f / (2.0f * RT_PI_R));
   float u = 0.5f + m_atan2(dir.z, dir.x) * inv_two_pi;
@@ -157,7 +181,7 @@ __device__ __forceinline__ V3 sheen_term(float sheen, V3 base, float sheen_tint,
 }
 
 // driver.c:350-409 with :287-348 inlined
-static __device__ __noinline__ void shade_pbr(const SceneDev &sc, const float *lut, int material, const ShadeIn &in, uint32_t &rng, ShadeOut &out) {
+RT_SHADE_PBR_FN void shade_pbr(const SceneDev &sc, const float *lut, int material, const ShadeIn &in, uint32_t &rng, ShadeOut &out) {
   const MaterialDev &mat = sc.materials[material];
 
   // driver.c:129-153

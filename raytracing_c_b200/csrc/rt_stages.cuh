@@ -402,8 +402,10 @@ __device__ __forceinline__ bool shade_hit(const SceneDev &sc, const float *texel
   return true;
 }
 
+// 64 registers (4 blocks per SM): the texel gathers are latency the extra warps cover — 2298 / 2073 / 2169 / 2610 us for
+// the bounce-0 launch of a 64-spp helmet chunk at 3 / 4 / 5 / 6 blocks
 #ifndef RT_SHADE_MIN_BLOCKS
-#define RT_SHADE_MIN_BLOCKS 3
+#define RT_SHADE_MIN_BLOCKS 4
 #endif
 __global__ void __launch_bounds__(256, RT_SHADE_MIN_BLOCKS)
 RT_KN(rt_shade_kernel)(const __grid_constant__ StageParams P) {
