@@ -43,14 +43,21 @@ struct ShadeOut { V3 dir, tint, emission; bool terminate; };
 
 __device__ __forceinline__ float rnd(uint32_t &state) { return rt_rand_f32(&state); }
 
-// lut[i] = (float)i / 255.999f, built once per block with the same IEEE division (driver.c:69-88)
-__device__ __forceinline__ V3 texel_rgb(const TextureDev &tex, const float *lut, int x, int y) {
-  uchar4 t = __ldg(&tex.texels[x + tex.width * y]);
-  return mk3(lut[t.x], lut[t.y], lut[t.z]);
+// driver.c:69-88: a texel byte b becomes (float)b / 255.999f.  Two instructions per channel, no table: PRMT drops the
+// byte into the mantissa of 2^23 (the float 8388608 + b, exact), one fused multiply-add forms (2^23 + b) * k - 2^23 * k
+// with k = RN(1 / 255.999f) — the exact sum is b * k, rounded once, and RN(b * k) equals the IEEE quotient for all 256
+// bytes (tests/csrc/texel_scale_check.c).
+__device__ __forceinline__ float texel_channel(unsigned rgba, unsigned selector) {
+  const float k = 1.0f / 255.999f;
+  return __fmaf_rn(__uint_as_float(__byte_perm(rgba, 0x4B000000u, selector)), k, -8388608.0f * k);
+}
+__device__ __forceinline__ V3 texel_rgb(const TextureDev &tex, int x, int y) {
+  const unsigned t = __ldg(reinterpret_cast<const unsigned *>(tex.texels) + (x + tex.width * y));
+  return mk3(texel_channel(t, 0x7650u), texel_channel(t, 0x7651u), texel_channel(t, 0x7652u));
 }
 
 // driver.c:49-93: negative wrap, fract, no half-texel offset, +1 neighbour clamped
-__device__ __forceinline__ V3 sample_bilinear_inline(const TextureDev &tex, const float *lut, float u, float v) {
+__device__ __forceinline__ V3 sample_bilinear_inline(const TextureDev &tex, float u, float v) {
   if (u < 0) u += (float)(-(int)u + 1);
   if (v < 0) v += (float)(-(int)v + 1);
   u = u - floorf(u);
@@ -68,13 +75,13 @@ __device__ __forceinline__ V3 sample_bilinear_inline(const TextureDev &tex, cons
     V3 bot = lerp3(mk3(t01.x, t01.y, t01.z), mk3(t11.x, t11.y, t11.z), a);
     return lerp3(top, bot, b);
   }
-  V3 top = lerp3(texel_rgb(tex, lut, x0, y0), texel_rgb(tex, lut, x1, y0), a);
-  V3 bot = lerp3(texel_rgb(tex, lut, x0, y1), texel_rgb(tex, lut, x1, y1), a);
+  V3 top = lerp3(texel_rgb(tex, x0, y0), texel_rgb(tex, x1, y0), a);
+  V3 bot = lerp3(texel_rgb(tex, x0, y1), texel_rgb(tex, x1, y1), a);
   return lerp3(top, bot, b);
 }
 
-static __device__ __noinline__ V3 sample_bilinear(const TextureDev &tex, const float *lut, float u, float v) {
-  return sample_bilinear_inline(tex, lut, u, v);
+static __device__ __noinline__ V3 sample_bilinear(const TextureDev &tex, float u, float v) {
+  return sample_bilinear_inline(tex, u, v);
 }
 
 // common.h:82-88.  The argument of the power is >= 0.055 / 1.055 (texel values are >= 0), so the
@@ -98,12 +105,12 @@ __device__ __forceinline__ V3 decode_srgb(V3 c) {
 }
 
 // driver.c:95-104 (asin argument clamped: DESIGN.md deviation list)
-__device__ __forceinline__ V3 environment(const SceneDev &sc, const float *lut, V3 dir) {
+__device__ __forceinline__ V3 environment(const SceneDev &sc, V3 dir) {
   float inv_pi     = (float)(1.0f / RT_PI_R);
   float inv_two_pi = (float)(1.0f / (2.0f * RT_PI_R));
   float u = 0.5f + m_atan2(dir.z, dir.x) * inv_two_pi;
   float v = 0.5f - m_asin(clamp1(dir.y, -1.0f, 1.0f)) * inv_pi;
-  return decode_srgb(sample_bilinear_inline(sc.textures[sc.env_texture], lut, u, v));
+  return decode_srgb(sample_bilinear_inline(sc.textures[sc.env_texture], u, v));
 }
 
 __device__ __forceinline__ float luma(V3 c) { return dot3(c, mk3(0.2126f, 0.7152f, 0.0722f)); }
@@ -172,13 +179,13 @@ __device__ __forceinline__ V3 sheen_term(float sheen, V3 base, float sheen_tint,
 }
 
 // driver.c:350-409 with :287-348 inlined
-__device__ __forceinline__ void shade_pbr(const SceneDev &sc, const float *lut, int material, const ShadeIn &in, uint32_t &rng, ShadeOut &out) {
+__device__ __forceinline__ void shade_pbr(const SceneDev &sc, int material, const ShadeIn &in, uint32_t &rng, ShadeOut &out) {
   const MaterialDev &mat = sc.materials[material];
 
   // driver.c:129-153
   V3 n = in.normal;
   if (mat.tex_normal >= 0) {
-    V3 s = sample_bilinear(sc.textures[mat.tex_normal], lut, in.u, in.v);
+    V3 s = sample_bilinear(sc.textures[mat.tex_normal], in.u, in.v);
     s = add3(scale3(s, 2.0f), mk3(-1, -1, -1));
     s.y *= -1;
     V3 t = in.tangent, b = in.bitangent;
@@ -189,11 +196,11 @@ __device__ __forceinline__ void shade_pbr(const SceneDev &sc, const float *lut, 
   }
 
   V3 base = mk3(mat.base[0], mat.base[1], mat.base[2]);
-  if (mat.tex_albedo >= 0) base = mul3(base, decode_srgb(sample_bilinear(sc.textures[mat.tex_albedo], lut, in.u, in.v)));
+  if (mat.tex_albedo >= 0) base = mul3(base, decode_srgb(sample_bilinear(sc.textures[mat.tex_albedo], in.u, in.v)));
 
   float roughness = mat.roughness, metalness = mat.metalness;
   if (mat.tex_mr >= 0) {
-    V3 mr = sample_bilinear(sc.textures[mat.tex_mr], lut, in.u, in.v);
+    V3 mr = sample_bilinear(sc.textures[mat.tex_mr], in.u, in.v);
     roughness *= mr.y;
     metalness *= mr.z;
   }
@@ -202,7 +209,7 @@ __device__ __forceinline__ void shade_pbr(const SceneDev &sc, const float *lut, 
   metalness /= 0.9f;
 
   V3 glow = mk3(mat.emission[0], mat.emission[1], mat.emission[2]);
-  if (mat.tex_emission >= 0) glow = mul3(glow, decode_srgb(sample_bilinear(sc.textures[mat.tex_emission], lut, in.u, in.v)));
+  if (mat.tex_emission >= 0) glow = mul3(glow, decode_srgb(sample_bilinear(sc.textures[mat.tex_emission], in.u, in.v)));
   out.emission = glow;
   out.terminate = false;
   out.tint = mk3(0, 0, 0);

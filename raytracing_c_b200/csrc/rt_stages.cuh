@@ -329,16 +329,11 @@ RT_KN(rt_trace_kernel)(const __grid_constant__ StageParams P) {
 // raytracer.c:554: background(direction) * tint + emission ends the path.
 __global__ void __launch_bounds__(256)
 RT_KN(rt_miss_kernel)(const __grid_constant__ StageParams P) {
-  __shared__ float texel_lut[256];
-  // u8 -> f32 texel table: the same IEEE division the reference does per tap
-  // (driver.c:69-88), done once per block instead of 12 times per bilinear fetch
-  texel_lut[threadIdx.x] = (float)threadIdx.x / 255.999f;
-  __syncthreads();
   const unsigned n = P.q.counts[P.bounce * Q_STRIDE + Q_MISSES];
   unsigned done = 0;
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const float4 a = P.q.miss_a[i];
-    V3 env = environment(P.scene, texel_lut, mk3(a.x, a.y, a.z));
+    V3 env = environment(P.scene, mk3(a.x, a.y, a.z));
     V3 radiance;
     if (P.bounce == 0) {
       // primary rays carry tint 1 and emission 0 (raytracer.c:507-510): their records are not stored;
@@ -363,7 +358,7 @@ RT_KN(rt_miss_kernel)(const __grid_constant__ StageParams P) {
 // queue of bounce + 1; paths that terminate or exhaust max_bounces (:557) write rad.
 // One surface interaction of cast_ray (raytracer.c:514-552) for the hit (t, u, v, slot) of the ray (o, d): returns
 // whether the path goes on; o, d, tint, emis and rng are updated in place (emis is the path's radiance if it ends).
-__device__ __forceinline__ bool shade_hit(const SceneDev &sc, const float *texel_lut, V3 &o, V3 &d, V3 &tint, V3 &emis,
+__device__ __forceinline__ bool shade_hit(const SceneDev &sc, V3 &o, V3 &d, V3 &tint, V3 &emis,
                                           uint32_t &rng, float hit_t, float hit_u, float hit_v, int slot,
                                           unsigned &c_shades, unsigned &c_pass) {
   const float4 *rec = sc.tri_rec + (size_t)slot * 7;
@@ -392,7 +387,7 @@ __device__ __forceinline__ bool shade_hit(const SceneDev &sc, const float *texel
   in.v = r4.w * w0 + r5.y * w1 + r5.w * w2;
   ShadeOut out;
   c_shades++;
-  shade_pbr(sc, texel_lut, __float_as_int(r6.x), in, rng, out);
+  shade_pbr(sc, __float_as_int(r6.x), in, rng, out);
   emis = add3(emis, mul3(out.emission, tint));          // raytracer.c:537
   if (out.terminate) return false;
   d = out.dir;
@@ -409,9 +404,6 @@ __device__ __forceinline__ bool shade_hit(const SceneDev &sc, const float *texel
 #endif
 __global__ void __launch_bounds__(256, RT_SHADE_MIN_BLOCKS)
 RT_KN(rt_shade_kernel)(const __grid_constant__ StageParams P) {
-  __shared__ float texel_lut[256];
-  texel_lut[threadIdx.x] = (float)threadIdx.x / 255.999f;
-  __syncthreads();
   const SceneDev &sc = P.scene;
   const unsigned lane = threadIdx.x & 31u;
   const unsigned n = P.q.counts[P.bounce * Q_STRIDE + Q_HITS];
@@ -434,7 +426,7 @@ RT_KN(rt_shade_kernel)(const __grid_constant__ StageParams P) {
         const float4 c = P.q.tint[path], e = P.q.emis[path];
         tint = mk3(c.x, c.y, c.z); emis = mk3(e.x, e.y, e.z);
       }
-      cont = shade_hit(sc, texel_lut, o, d, tint, emis, rng, h.x, h.y, h.z, __float_as_int(h.w), c_shades, c_pass);
+      cont = shade_hit(sc, o, d, tint, emis, rng, h.x, h.y, h.z, __float_as_int(h.w), c_shades, c_pass);
       if (P.bounce + 1 >= P.max_bounces) cont = false;        // raytracer.c:557
       if (!cont) {
         P.q.rad[path] = make_float4(emis.x, emis.y, emis.z, 0);

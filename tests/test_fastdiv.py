@@ -24,3 +24,13 @@ def test_fma_division_by_1p055_is_the_ieee_quotient(tmp_path):
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout
     assert out.stdout.strip().endswith("ok")
+
+
+def test_texel_byte_to_float_by_fma_is_the_ieee_quotient(tmp_path):
+    """rt_shade.cuh texel_channel: PRMT into the mantissa of 2^23 + one fused multiply-add == (float)b / 255.999f for all bytes."""
+    exe = tmp_path / "texel_scale_check"
+    subprocess.run(["gcc", "-O2", "-ffp-contract=off", "-mfma", "-o", str(exe),
+                    os.path.join(ROOT, "tests", "csrc", "texel_scale_check.c"), "-lm"], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout
+    assert out.stdout.strip().endswith("ok")
