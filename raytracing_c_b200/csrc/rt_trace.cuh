@@ -18,6 +18,7 @@
 #define RT_BLOCK 256
 #endif
 
+
 // raytracer.c:190-230 for ONE child box, general form: the reference's nested MINPS/MAXPS with
 // their "second operand when unordered" rule, as operand-order selects.  Needed only when a
 // reciprocal direction component is infinite (0 * inf = NaN lanes, raytracer.c:212-225).
