@@ -153,6 +153,7 @@ struct HostScene {
   int   env_slot = -1;
   int   depth = 0, n_internal = 0, n_slots = 0;
   float root_lo[3], root_hi[3];
+  int   root_upper_empty = 0;             // children 4..7 of the root are padding (lo == hi on every axis)
   Fingerprint fp;
 };
 
@@ -259,11 +260,13 @@ static int flatten(const Scene *scene, HostScene &hs) {
 
   // union of the root's child boxes; all-zero padding slots (lo == hi) can never be entered (enter >= leave)
   for (int a = 0; a < 3; a++) { hs.root_lo[a] = INFINITY; hs.root_hi[a] = -INFINITY; }
+  hs.root_upper_empty = 1;
   for (int j = 0; j < 8; j++) {
     const float *n0 = hs.nodes;
     bool empty = true;
     for (int a = 0; a < 3; a++) empty &= (n0[a * 8 + j] == n0[(3 + a) * 8 + j]);
     if (empty) continue;
+    if (j >= 4) hs.root_upper_empty = 0;
     for (int a = 0; a < 3; a++) {
       hs.root_lo[a] = fminf(hs.root_lo[a], n0[a * 8 + j]);
       hs.root_hi[a] = fmaxf(hs.root_hi[a], n0[(3 + a) * 8 + j]);
@@ -276,6 +279,7 @@ static void fill_common(const HostScene &hs, SceneDev &dev) {
   dev.env_texture = hs.env_slot;
   dev.depth = hs.depth; dev.n_internal = hs.n_internal; dev.n_slots = hs.n_slots;
   for (int a = 0; a < 3; a++) { dev.root_lo[a] = hs.root_lo[a]; dev.root_hi[a] = hs.root_hi[a]; }
+  dev.root_upper_empty = hs.root_upper_empty;
 }
 
 static int make_events(DeviceScene &ds) {

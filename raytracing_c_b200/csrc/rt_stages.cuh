@@ -33,6 +33,9 @@
 #define RT_TRACE_WIDE_BOUNCES 2
 #endif
 #define RT_FULL 0xffffffffu
+#ifndef RT_ROOT_STEP_AT_REFILL
+#define RT_ROOT_STEP_AT_REFILL 1
+#endif
 
 // counts[bounce][...]: queue lengths written by one stage and read by the next
 enum { Q_RAYS = 0, Q_HITS, Q_MISSES, Q_FETCH, Q_STRIDE = 4 };
@@ -279,6 +282,10 @@ RT_KN(rt_trace_kernel)(const __grid_constant__ StageParams P) {
             walk_begin(w, sc, ox, oy, oz, dx, dy, dz);
             c_rays++;
             if (walk_misses_root<PRIMARY>(w, sc)) { w.flags = WALK_RAY; c_nodes++; c_root_miss++; }      // the root visit, nothing entered
+#if RT_ROOT_STEP_AT_REFILL
+            // the root visit here, among the lanes that just took a ray (all at the same node), instead of in a voted turn
+            else walk_node_step<PRIMARY, true>(w, sc, levels, c_nodes);
+#endif
           }
         }
         range_next += take;

@@ -68,14 +68,18 @@ __device__ __forceinline__ float child_entry_regular(float nx, float ny, float n
 #define RT_ROW_X_SUM  6u     // near + far vector index of an axis: 0 + 6, 2 + 8, 4 + 10
 #define RT_ROW_Y_SUM 10u
 #define RT_ROW_Z_SUM 14u
+// `upper` false: children 4..7 are known padding boxes (lo == hi on every axis).  Their near and far plane coincide,
+// so enter = max(EPS, a, b, c) >= a >= min(t_max, a, b, c) = leave whatever the ray: the reference's test yields +inf
+// for them, and so does skipping it.
 template <bool REL>
 __device__ __forceinline__ void node_entries_regular(const float4 *__restrict__ nb, unsigned onx, unsigned ony, unsigned onz,
                                                      float ox, float oy, float oz, float ix, float iy, float iz,
-                                                     float t_max, float (&e)[8]) {
+                                                     float t_max, float (&e)[8], bool upper = true) {
   const float4 *pnx = nb + onx, *pny = nb + ony, *pnz = nb + onz;
   const float4 *pfx = nb + (RT_ROW_X_SUM - onx), *pfy = nb + (RT_ROW_Y_SUM - ony), *pfz = nb + (RT_ROW_Z_SUM - onz);
   #pragma unroll
   for (int h = 0; h < 2; h++) {
+    if (h == 1 && !upper) { e[4] = e[5] = e[6] = e[7] = CUDART_INF_F; break; }
     float4 nx = __ldg(pnx + h), ny = __ldg(pny + h), nz = __ldg(pnz + h);
     float4 fx = __ldg(pfx + h), fy = __ldg(pfy + h), fz = __ldg(pfz + h);
     e[4 * h + 0] = child_entry_regular<REL>(nx.x, ny.x, nz.x, fx.x, fy.x, fz.x, ox, oy, oz, ix, iy, iz, t_max);
@@ -177,17 +181,21 @@ __device__ __forceinline__ bool walk_misses_root(const RayWalk &w, const SceneDe
 
 // One node step: (box-test the node just entered,) pick the next child; ends with a leaf to test,
 // a child to enter on the next step, or the walk finished.
-template <bool REL>
+// ROOT: the step is the walk's first (the caller guarantees w.node == 0 with its box test pending): the root's upper
+// four children are skipped when the scene's are padding (a 15 000-triangle model fills four of the root's eight).
+template <bool REL, bool ROOT = false>
 __device__ __forceinline__ void walk_node_step(RayWalk &w, const SceneDev &sc, float4 *levels, unsigned &c_nodes) {
   float (&e)[8] = w.e;
   for (;;) {
     if (w.flags & WALK_BOX) {
       if (w.flags & WALK_REG) {
-        if (REL) node_entries_regular<true >((const float4 *)sc.nodes_rel + (size_t)w.node * 12, w.onx, w.ony, w.onz, 0, 0, 0, w.ix, w.iy, w.iz, w.hit_t, e);
+        const bool upper = !ROOT || !sc.root_upper_empty;
+        const size_t first = ROOT ? 0 : (size_t)w.node * 12;
+        if (REL) node_entries_regular<true >((const float4 *)sc.nodes_rel + first, w.onx, w.ony, w.onz, 0, 0, 0, w.ix, w.iy, w.iz, w.hit_t, e, upper);
 #if defined(RT_FAST) && RT_FAST
-        else     node_entries_regular<false>((const float4 *)sc.nodes + (size_t)w.node * 12, w.onx, w.ony, w.onz, -w.ox * w.ix, -w.oy * w.iy, -w.oz * w.iz, w.ix, w.iy, w.iz, w.hit_t, e);
+        else     node_entries_regular<false>((const float4 *)sc.nodes + first, w.onx, w.ony, w.onz, -w.ox * w.ix, -w.oy * w.iy, -w.oz * w.iz, w.ix, w.iy, w.iz, w.hit_t, e, upper);
 #else
-        else     node_entries_regular<false>((const float4 *)sc.nodes + (size_t)w.node * 12, w.onx, w.ony, w.onz, w.ox, w.oy, w.oz, w.ix, w.iy, w.iz, w.hit_t, e);
+        else     node_entries_regular<false>((const float4 *)sc.nodes + first, w.onx, w.ony, w.onz, w.ox, w.oy, w.oz, w.ix, w.iy, w.iz, w.hit_t, e, upper);
 #endif
       } else {
         const Entries8 r = node_entries_any((const float4 *)(sc.nodes + (size_t)w.node * 48), w.ox, w.oy, w.oz, w.ix, w.iy, w.iz, w.hit_t);
