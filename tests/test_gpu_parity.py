@@ -87,6 +87,41 @@ def test_radiance_exact_vs_oracle(name, w, h, spp):
         loaded.close()
 
 
+def _write_triangle_soup(path, n_triangles, seed):
+    """An OBJ of small random triangles in a 4 x 4 x 4 cube (no normals, no material file)."""
+    rng = np.random.default_rng(seed)
+    centre = rng.uniform(-2.0, 2.0, size=(n_triangles, 1, 3))
+    verts = (centre + rng.uniform(-0.06, 0.06, size=(n_triangles, 3, 3))).reshape(-1, 3)
+    with open(path, "w") as f:
+        f.write("".join(f"v {x:.6f} {y:.6f} {z:.6f}\n" for x, y, z in verts))
+        f.write("".join(f"f {3 * i + 1} {3 * i + 2} {3 * i + 3}\n" for i in range(n_triangles)))
+
+
+@pytest.mark.parametrize("n_triangles,expect_root_children", [(30000, 8), (9000, 3)])
+def test_generated_scene_full_and_sparse_root(tmp_path, n_triangles, expect_root_children):
+    """The trace kernel skips the box tests of the root's padding children (rt_trace.cuh, walk_node_step<ROOT>).  The shipped
+    models fill at most four of the root's eight children; 30 000 triangles fill all eight (depth 4 holds 32 768), 9 000
+    fill three.  Radiance, primary-hit slots and the node / leaf visit counters must equal the oracle's on both."""
+    path = str(tmp_path / f"soup_{n_triangles}.obj")
+    _write_triangle_soup(path, n_triangles, seed=n_triangles)
+    cam = driver.look_at(eye=(0.3, 0.4, 6.0), target=(0.0, 0.0, 0.0))
+    loaded = driver.load_scene(path, shader_proc=oracle_ffi.shader_proc(), background_proc=oracle_ffi.background_proc(), camera=cam)
+    try:
+        n_int = loaded.scene.bvh.last_row_offset
+        import ctypes as C
+        root = np.ctypeslib.as_array(C.cast(loaded.scene.bvh.nodes.data, C.POINTER(C.c_float)), shape=(n_int, 6, 8))[0]
+        assert int((root[:3] != root[3:]).any(axis=0).sum()) == expect_root_children
+        w, h, spp = 160, 120, 4
+        got = gpu_render(loaded, w, h, spp)
+        ref = oracle_ffi.render(loaded, w, h, spp, n_threads=8, want_hit_ids=True)
+        assert (ref["hit_ids"] >= 0).sum() > 1000, "camera must see the triangles"
+        assert np.array_equal(got["hit_ids"], ref["hit_ids"])
+        assert np.array_equal(got["accum"], ref["accum"])
+        assert got["counters"] == ref["counters"]
+    finally:
+        loaded.close()
+
+
 @pytest.mark.parametrize("sheen_tint", [0.0, 1.0])
 def test_sheen_injected_and_denoised(sheen_tint):
     """BASELINE config 4: sheen.glb carries no KHR_materials_sheen, so sheen is injected."""
