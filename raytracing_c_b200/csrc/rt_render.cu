@@ -181,6 +181,7 @@ static size_t counts_bytes(int max_bounces) {
 static size_t chunk_paths_max() {
   if (const char *e = getenv("RT_GPU_CHUNK_PATHS")) {
     unsigned long long v = strtoull(e, nullptr, 10);
+    if (v > (1ull << 31)) v = 1ull << 31;          // path ids and queue lengths are 32-bit
     if (v > 0) return (size_t)v;
   }
   return RT_CHUNK_PATHS_MAX;
