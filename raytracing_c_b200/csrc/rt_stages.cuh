@@ -146,7 +146,7 @@ __device__ __forceinline__ unsigned warp_append(unsigned *count, bool want, unsi
 // 32x32 chunk queue, raytracer.c:619-627) and keep their lanes full: whenever RT_REFILL_MIN_*
 // lanes have finished, those lanes append their results to the HIT / MISS queues and take the
 // next rays, while the others keep their walk state.  PRIMARY: the ray is generated from the
-// path id — 32 consecutive ids are one 8x4 pixel tile at one sample index, so rays are coherent.
+// path id — 32 consecutive ids are 32 samples of one pixel (RT_PATH_LAYOUT 1), so a warp's rays are coherent.
 #ifndef RT_MIN_BATCH
 #define RT_MIN_BATCH 4u
 #endif
