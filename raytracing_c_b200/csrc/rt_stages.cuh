@@ -33,6 +33,12 @@
 #define RT_TRACE_WIDE_BOUNCES 2
 #endif
 #define RT_FULL 0xffffffffu
+// rays a warp reserves per atomic on a long queue: 5823 / 5500 / 5372 / 5411 / 5831 us for the primary trace of a 64-spp helmet
+// chunk at 64 / 128 / 256 / 512 / 1024 (consecutive ids are neighbouring pixels: short shares scatter a warp over the image
+// and lose L1 reuse, long ones unbalance the last wave)
+#ifndef RT_BATCH_MAX
+#define RT_BATCH_MAX 256u
+#endif
 #ifndef RT_ROOT_STEP_AT_REFILL
 #define RT_ROOT_STEP_AT_REFILL 1
 #endif
@@ -189,7 +195,7 @@ RT_KN(rt_trace_kernel)(const __grid_constant__ StageParams P) {
   // spread over all warps of the grid
   const unsigned total_warps = gridDim.x * (RT_BLOCK / 32);
   unsigned batch = (n_in / (total_warps * 4u)) & ~31u;
-  if (batch > 256u) batch = 256u;
+  if (batch > RT_BATCH_MAX) batch = RT_BATCH_MAX;
   if (batch < 32u) {
     // a short queue: one share per warp, so the kernel lasts as long as a few rays, not as 32 in lock step
     batch = (n_in + total_warps - 1u) / total_warps;
