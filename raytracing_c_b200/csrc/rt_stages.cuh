@@ -174,7 +174,7 @@ __device__ __forceinline__ unsigned warp_append(unsigned *count, bool want, unsi
 template <bool PRIMARY, int MIN_BLOCKS = (PRIMARY ? RT_TRACE_MIN_BLOCKS_PRIMARY : RT_TRACE_MIN_BLOCKS)>
 __global__ void __launch_bounds__(RT_BLOCK, MIN_BLOCKS)
 RT_KN(rt_trace_kernel)(const __grid_constant__ StageParams P) {
-  extern __shared__ float4 level_store[];          // [depth][2][RT_BLOCK] entry distances of pending levels
+  extern __shared__ float4 level_store[];          // [depth - 1][2][RT_BLOCK] entry distances of pending levels (2 .. depth)
   const SceneDev &sc = P.scene;
   const unsigned lane = threadIdx.x & 31u;
   const unsigned lt_mask = (1u << lane) - 1u;

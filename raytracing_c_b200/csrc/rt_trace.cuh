@@ -117,7 +117,8 @@ __device__ __forceinline__ float min8(const float (&e)[8]) {
 }
 
 // per-thread slice of the level store: levels[(level - 1) * 2 + half][tid]
-#define RT_LEVELS(level, half) levels[(((level) - 1) * 2 + (half)) * RT_BLOCK]
+// (levels 2 .. depth: a node of level 1 hands out leaves and never parks its entries — its slot is not allocated)
+#define RT_LEVELS(level, half) levels[(((level) - 2) * 2 + (half)) * RT_BLOCK]
 
 // raytracer.c:443-503: closest hit of one ray, one thread per ray, as a resumable walk.
 // The reference recursion (8 entry distances per level on the C stack, up to 8 selection
