@@ -36,6 +36,9 @@
 // rays a warp reserves per atomic on a long queue: 5823 / 5500 / 5372 / 5411 / 5831 us for the primary trace of a 64-spp helmet
 // chunk at 64 / 128 / 256 / 512 / 1024 (consecutive ids are neighbouring pixels: short shares scatter a warp over the image
 // and lose L1 reuse, long ones unbalance the last wave)
+#ifndef RT_EMIT_ONE_ATOMIC
+#define RT_EMIT_ONE_ATOMIC 1
+#endif
 #ifndef RT_BATCH_MAX
 #define RT_BATCH_MAX 256u
 #endif
@@ -44,7 +47,8 @@
 #endif
 
 // counts[bounce][...]: queue lengths written by one stage and read by the next
-enum { Q_RAYS = 0, Q_HITS, Q_MISSES, Q_FETCH, Q_STRIDE = 4 };
+// (HITS and MISSES share one aligned 64-bit word: the trace kernel reserves both with one atomic)
+enum { Q_RAYS = 0, Q_FETCH = 1, Q_HITS = 2, Q_MISSES = 3, Q_STRIDE = 4 };
 
 struct PathQueues {
   // queue records, compacted (a record moves with its ray): what the traversal needs and nothing else
@@ -226,8 +230,21 @@ RT_KN(rt_trace_kernel)(const __grid_constant__ StageParams P) {
             rng  = __float_as_uint(b.w);
           }
         }
+#if RT_EMIT_ONE_ATOMIC
+        // slots in the HIT and the MISS queue with ONE atomic: the two lengths are the halves of an aligned 64-bit word
+        // (a queue is shorter than 2^31, the low half cannot carry into the high one)
+        const unsigned hmask = __ballot_sync(RT_FULL, is_hit), mmask = __ballot_sync(RT_FULL, is_miss);
+        unsigned long long both = 0;
+        if (lane == 0)
+          both = atomicAdd(reinterpret_cast<unsigned long long *>(&counts[Q_HITS]),
+                           (unsigned long long)__popc(hmask) | ((unsigned long long)__popc(mmask) << 32));
+        both = __shfl_sync(RT_FULL, both, 0);
+        const unsigned hpos = (unsigned)both + (unsigned)__popc(hmask & lt_mask);
+        const unsigned mpos = (unsigned)(both >> 32) + (unsigned)__popc(mmask & lt_mask);
+#else
         const unsigned hpos = warp_append(&counts[Q_HITS], is_hit, lane);
         const unsigned mpos = warp_append(&counts[Q_MISSES], is_miss, lane);
+#endif
         if (is_hit) {
           P.q.hit_a[hpos] = make_float4(w.ox, w.oy, w.oz, w.dx);
           P.q.hit_b[hpos] = make_float4(w.dy, w.dz, __uint_as_float(path), __uint_as_float(rng));
