@@ -139,11 +139,16 @@ rt_reduce_resolve_kernel(const ReduceParts parts, float *__restrict__ sum_out, i
   if (n_here == 4) {
     #pragma unroll
     for (int q = 0; q < 3; q++) {
-      float4 s = reinterpret_cast<const float4 *>(parts.part[0])[3 * g + q];
-      for (int k = 1; k < parts.n; k++) {
-        const float4 t = reinterpret_cast<const float4 *>(parts.part[k])[3 * g + q];
-        s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
-      }
+      // every part's vector is requested before the first add (a peer's accumulator is a ~2 us round trip over NVLink:
+      // the loop over parts, left rolled, waited for each in turn); the sum itself stays in rank order
+      float4 t[RT_MAX_PARTS];
+      #pragma unroll
+      for (int k = 0; k < RT_MAX_PARTS; k++)
+        if (k < parts.n) t[k] = reinterpret_cast<const float4 *>(parts.part[k])[3 * g + q];
+      float4 s = t[0];
+      #pragma unroll
+      for (int k = 1; k < RT_MAX_PARTS; k++)
+        if (k < parts.n) { s.x += t[k].x; s.y += t[k].y; s.z += t[k].z; s.w += t[k].w; }
       v[4 * q] = s.x; v[4 * q + 1] = s.y; v[4 * q + 2] = s.z; v[4 * q + 3] = s.w;
       if (sum_out) reinterpret_cast<float4 *>(sum_out)[3 * g + q] = s;
     }
