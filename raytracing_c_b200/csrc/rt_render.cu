@@ -34,10 +34,10 @@
 #include "rt_kernels.h"
 
 // rt_render_fast.cu: the same bounce-stage kernels compiled with FMA contraction and hardware transcendentals
-void rt_fast_launch_trace(const StageParams &P, unsigned grid, size_t smem, cudaStream_t stream);
+void rt_fast_launch_trace(const StageParams &P, unsigned grid, size_t smem, cudaStream_t stream, bool wide);
 void rt_fast_launch_miss(const StageParams &P, unsigned grid, cudaStream_t stream);
 void rt_fast_launch_shade(const StageParams &P, unsigned grid, cudaStream_t stream);
-int  rt_fast_trace_setup(size_t level_bytes);
+int  rt_fast_trace_setup(size_t level_bytes, int *wide_blocks_per_sm);
 
 // ------------------------------------------------------------ camera-relative scene
 // All primary rays start at the camera origin o (raytracer.c:612).  Everything in the slab and
@@ -224,7 +224,7 @@ size_t rt_render_workspace_bytes(int width, int height, int n_samples, int max_b
 }
 
 // occupancy of the trace kernel and its dynamic-shared-memory opt-in, per device (cudaFuncSetAttribute is per device)
-static int g_trace_blocks_per_sm[RT_MAX_DEVICES], g_wide_blocks_per_sm[RT_MAX_DEVICES], g_primary_blocks_per_sm[RT_MAX_DEVICES], g_fast_blocks_per_sm[RT_MAX_DEVICES];
+static int g_trace_blocks_per_sm[RT_MAX_DEVICES], g_wide_blocks_per_sm[RT_MAX_DEVICES], g_primary_blocks_per_sm[RT_MAX_DEVICES], g_fast_blocks_per_sm[RT_MAX_DEVICES], g_fast_wide_blocks_per_sm[RT_MAX_DEVICES];
 static size_t g_level_bytes[RT_MAX_DEVICES];
 
 // ---- optional per-stage timing (bench.py's roofline leg): CUDA events around every launch, on the
@@ -299,7 +299,7 @@ static int trace_launch_setup(const SceneDev &scene, int *dev_out, size_t *level
     cudaFuncSetAttribute(rt_trace_kernel<false, RT_TRACE_MIN_BLOCKS_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, RT_MAX_DEPTH * 2 * RT_BLOCK * 16);
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, rt_trace_kernel<false, RT_TRACE_MIN_BLOCKS_WIDE>, RT_BLOCK, level_bytes) != cudaSuccess || n < 1) n = 1;
     g_wide_blocks_per_sm[dev] = n;
-    g_fast_blocks_per_sm[dev] = rt_fast_trace_setup(level_bytes);
+    g_fast_blocks_per_sm[dev] = rt_fast_trace_setup(level_bytes, &g_fast_wide_blocks_per_sm[dev]);
     g_level_bytes[dev] = level_bytes;
   }
   *dev_out = dev;
@@ -356,6 +356,7 @@ int rt_launch_render(const RenderParams &p, int sm_count, void *workspace, size_
   const unsigned wide_grid = (unsigned)(sm_count * g_wide_blocks_per_sm[dev]);
   const unsigned primary_grid = (unsigned)(sm_count * g_primary_blocks_per_sm[dev]);
   const unsigned fast_grid = (unsigned)(sm_count * g_fast_blocks_per_sm[dev]);
+  const unsigned fast_wide_grid = (unsigned)(sm_count * g_fast_wide_blocks_per_sm[dev]);
   // grid-stride kernels (miss, shade, accumulate): blocks per SM by queue length.  The items of a queue cost unevenly
   // (texture taps, lobe picks), so the long queues of the first bounces want many short-lived blocks to even out the
   // last wave (bounce-0 miss 2073 / 1950 / 1889 / 1864 / 1856 us at 8 / 16 / 32 / 64 / 128 blocks per SM), the short late
@@ -384,7 +385,7 @@ int rt_launch_render(const RenderParams &p, int sm_count, void *workspace, size_
       const int bslot = b < RT_STAGE_BOUNCES ? b : RT_STAGE_BOUNCES - 1;
       if (b > 0) {
         StageTimer t(RT_STAGE_TRACE * RT_STAGE_BOUNCES + bslot, stream, dev);
-        if (p.fast) rt_fast_launch_trace(P, fast_grid, level_bytes, stream);
+        if (p.fast) rt_fast_launch_trace(P, b <= RT_TRACE_WIDE_BOUNCES ? fast_wide_grid : fast_grid, level_bytes, stream, b <= RT_TRACE_WIDE_BOUNCES);
         else if (b <= RT_TRACE_WIDE_BOUNCES) rt_trace_kernel<false, RT_TRACE_MIN_BLOCKS_WIDE><<<wide_grid, RT_BLOCK, level_bytes, stream>>>(P);
         else        rt_trace_kernel<false><<<trace_grid, RT_BLOCK, level_bytes, stream>>>(P);
         launches++;

@@ -11,8 +11,9 @@
 #include "rt_stages.cuh"
 #include "rt_kernels.h"
 
-void rt_fast_launch_trace(const StageParams &P, unsigned grid, size_t smem, cudaStream_t stream) {
-  rt_trace_kernel_fast<false><<<grid, RT_BLOCK, smem, stream>>>(P);
+void rt_fast_launch_trace(const StageParams &P, unsigned grid, size_t smem, cudaStream_t stream, bool wide) {
+  if (wide) rt_trace_kernel_fast<false, RT_TRACE_MIN_BLOCKS_WIDE><<<grid, RT_BLOCK, smem, stream>>>(P);
+  else      rt_trace_kernel_fast<false><<<grid, RT_BLOCK, smem, stream>>>(P);
 }
 
 void rt_fast_launch_miss(const StageParams &P, unsigned grid, cudaStream_t stream) {
@@ -23,9 +24,12 @@ void rt_fast_launch_shade(const StageParams &P, unsigned grid, cudaStream_t stre
   rt_shade_kernel_fast<<<grid, 256, 0, stream>>>(P);
 }
 
-int rt_fast_trace_setup(size_t level_bytes) {
-  int n = 0;
+int rt_fast_trace_setup(size_t level_bytes, int *wide_blocks_per_sm) {
+  int n = 0, w = 0;
   cudaFuncSetAttribute(rt_trace_kernel_fast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RT_MAX_DEPTH * 2 * RT_BLOCK * 16);
+  cudaFuncSetAttribute(rt_trace_kernel_fast<false, RT_TRACE_MIN_BLOCKS_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, RT_MAX_DEPTH * 2 * RT_BLOCK * 16);
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, rt_trace_kernel_fast<false>, RT_BLOCK, level_bytes) != cudaSuccess || n < 1) n = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w, rt_trace_kernel_fast<false, RT_TRACE_MIN_BLOCKS_WIDE>, RT_BLOCK, level_bytes) != cudaSuccess || w < 1) w = 1;
+  *wide_blocks_per_sm = w;
   return n;
 }
