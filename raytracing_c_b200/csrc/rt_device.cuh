@@ -57,6 +57,7 @@ struct SceneDev {
   int                env_texture;
   int                depth, n_internal, n_slots;
   float              root_lo[3], root_hi[3];   // union of the root's non-empty child boxes (rt_trace.cuh)
+  float              srgb_of_zero;             // decode_srgb(0): the sRGB decode of a black texel (rt_shade.cuh)
   int                root_upper_empty;         // the root's children 4..7 are padding boxes (lo == hi): never entered
   float              view[3][4];      // rows 0..2 of the camera-to-world matrix
   float              focal_length;

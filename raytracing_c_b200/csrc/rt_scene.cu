@@ -280,6 +280,7 @@ static void fill_common(const HostScene &hs, SceneDev &dev) {
   dev.depth = hs.depth; dev.n_internal = hs.n_internal; dev.n_slots = hs.n_slots;
   for (int a = 0; a < 3; a++) { dev.root_lo[a] = hs.root_lo[a]; dev.root_hi[a] = hs.root_hi[a]; }
   dev.root_upper_empty = hs.root_upper_empty;
+  dev.srgb_of_zero = rt_powf_positive((0.0f + 0.055f) / 1.055f, 2.4f);      // rt_math.h: the same bits on host and device
 }
 
 static int make_events(DeviceScene &ds) {

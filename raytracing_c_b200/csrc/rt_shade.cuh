@@ -209,7 +209,15 @@ __device__ __forceinline__ void shade_pbr(const SceneDev &sc, int material, cons
   metalness /= 0.9f;
 
   V3 glow = mk3(mat.emission[0], mat.emission[1], mat.emission[2]);
-  if (mat.tex_emission >= 0) glow = mul3(glow, decode_srgb(sample_bilinear(sc.textures[mat.tex_emission], in.u, in.v)));
+  if (mat.tex_emission >= 0) {
+    // emissive maps are mostly black, and a black bilinear tap decodes to one constant (common.h:82-88 has no linear toe:
+    // pow(0.055 / 1.055, 2.4)) — sc.srgb_of_zero holds it, evaluated once by the same rt_math.h code, so a warp whose
+    // taps are all black skips its three pow
+    const V3 e = sample_bilinear(sc.textures[mat.tex_emission], in.u, in.v);
+    const bool black = (e.x == 0.0f) & (e.y == 0.0f) & (e.z == 0.0f);
+    const V3 lin = black ? mk3(sc.srgb_of_zero, sc.srgb_of_zero, sc.srgb_of_zero) : decode_srgb(e);
+    glow = mul3(glow, lin);
+  }
   out.emission = glow;
   out.terminate = false;
   out.tint = mk3(0, 0, 0);
