@@ -151,6 +151,27 @@ def test_anisotropic_material():
         loaded.close()
 
 
+def test_random_image_shapes_sample_counts_and_chunks(monkeypatch):
+    """Random widths, heights, sample counts, bounce limits and wavefront-chunk sizes (odd ones included): the path id ->
+    (pixel, sample) and tile -> (x, y) decode divides by multiply-high with per-launch magic numbers (rt_fastdiv.h), the
+    samples of a chunk and the tiles of a row are the divisors.  Radiance, primary-hit slots and counters equal the oracle's."""
+    rng = np.random.default_rng(20261018)
+    loaded = load("spheres.glb")
+    try:
+        for _ in range(12):
+            w, h = int(rng.integers(1, 200)), int(rng.integers(1, 140))
+            spp, bounces = int(rng.integers(1, 24)), int(rng.integers(1, 9))
+            per_sample = ((w + 7) // 8) * ((h + 3) // 4) * 32
+            monkeypatch.setenv("RT_GPU_CHUNK_PATHS", str(per_sample * int(rng.integers(1, spp + 1))))
+            got = gpu_render(loaded, w, h, spp, bounces)
+            ref = oracle_ffi.render(loaded, w, h, spp, bounces, n_threads=8, want_hit_ids=True)
+            assert np.array_equal(got["hit_ids"], ref["hit_ids"]), (w, h, spp, bounces)
+            assert np.array_equal(got["accum"], ref["accum"]), (w, h, spp, bounces)
+            assert got["counters"] == ref["counters"], (w, h, spp, bounces)
+    finally:
+        loaded.close()
+
+
 @pytest.mark.parametrize("shape", [(1, 1), (7, 5), (33, 31), (64, 64), (257, 130)])
 def test_denoiser_byte_exact_random(shape):
     h, w = shape
