@@ -591,7 +591,7 @@ def run_gpu(args) -> None:
                 "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": dict(workload_config(args, f"{mode_name} split x{world} (the library's policy, rt_gpu_render_shard_device); film: {film}"),
                                l2="flushed between steps (256 MiB memset inside the timed region, ~0.05 ms)",
-                               chunk="the library renders as many samples of every pixel per wavefront chunk as its path queues hold (256 Mi paths by default = 128 spp at 1080p)",
+                               chunk="the library renders as many samples of every pixel per wavefront chunk as its path queues hold (512 Mi paths by default = 256 spp at 1080p)",
                                host_buffers="pinned (rt_gpu_host_alloc)" if not args.pageable else "pageable (staged through a pinned ring)",
                                arithmetic="FAST MODE (opt-in): bounce stages FMA-contracted with hardware transcendentals; primary hits, ray generation, film exact"
                                if args.fast else "exact: every sample bit-identical to the reference arithmetic (no FMA contraction, rt_math.h)"),

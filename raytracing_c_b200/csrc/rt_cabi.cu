@@ -320,7 +320,7 @@ void rt_gpu_host_free(void *p) {
 }
 
 // Allocates what a frame of this size will need (accumulators, image, path-queue workspace on every device) ahead of
-// the first render, so the allocations (tens of ms for a 34 GB workspace) can overlap the host's model load.
+// the first render, so the allocations (tens of ms for a 69 GB workspace) can overlap the host's model load.
 int rt_gpu_prepare_frame(isize width, isize height, isize samples, isize max_bounces) {
   std::lock_guard<std::mutex> lock(g_mutex);
   if (ensure_init()) return 1;

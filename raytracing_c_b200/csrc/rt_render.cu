@@ -171,18 +171,19 @@ rt_reduce_resolve_kernel(const ReduceParts parts, float *__restrict__ sum_out, i
 
 // ------------------------------------------------------------------- launchers
 #define RT_PATH_BYTES ((2 + 3 + 1 + 2) * sizeof(float4))       // ray + hit + miss records and the tint / emission(=rad) state of one path
-#define RT_CHUNK_PATHS_MAX (256u << 20)
+#define RT_CHUNK_PATHS_MAX (512u << 20)
 
 static size_t counts_bytes(int max_bounces) {
   size_t b = (size_t)(max_bounces + 1) * Q_STRIDE * sizeof(unsigned);
   return (b + 255) & ~(size_t)255;
 }
 
-// Paths per wavefront chunk.  Every chunk pays a fixed ~1.5 ms: the late bounces hold a few 10^4..10^5 rays and
-// their kernels last as long as their slowest warp (b3..b7: 1.6 ms per chunk whatever its size).  Measured on
-// helmet 1080p (round 2, 128 B per path): 6.18 / 6.28 / 6.33 Gsamples/s at 128 / 256 / 512 Mi paths.  Default
-// 256 Mi paths = 34 GB of the 180 GB on the device; a device that cannot spare it gets smaller chunks (rt_cabi.cu).
-// RT_GPU_CHUNK_PATHS overrides it (tuning / tests).
+// Paths per wavefront chunk.  Every chunk pays a fixed cost: the late bounces hold a few 10^4..10^5 rays and their
+// kernels last as long as their slowest warp whatever the chunk's size.  Measured on helmet 1080p x 1024 spp with the
+// final kernels of round 2 (128 B per path): 7.00 / 7.16 / 7.25 Gsamples/s at 128 / 256 / 512 Mi paths.  Default
+// 512 Mi paths = 69 GB of the 180 GB on the device (a 1080p frame: 256 samples of every pixel per chunk); a device
+// that cannot spare it gets smaller chunks (rt_cabi.cu halves the request until it fits).  Path ids are 32-bit: 2^31
+// is the ceiling.  RT_GPU_CHUNK_PATHS overrides it (tuning / tests).
 static size_t chunk_paths_max() {
   if (const char *e = getenv("RT_GPU_CHUNK_PATHS")) {
     unsigned long long v = strtoull(e, nullptr, 10);
